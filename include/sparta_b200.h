@@ -1,0 +1,207 @@
+/* sparta_b200 -- C ABI of the B200 (sm_100a) block-sparse x dense multiply.
+ *
+ * Drop-in boundary for the SpMM hot path of HicrestLaboratory/SPARTA.  Each
+ * entry point states the reference interface it replaces (paths relative to the
+ * reference checkout).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions shared with the reference (include/definitions.h:4-6):
+ *   intT  = int64_t ("long"),  DataT = DataT_C = float.
+ *   C = A*B with alpha = beta = 1 on a caller-zeroed C (test/cuda/cuda_multiply.cpp:134).
+ *   The reference never uploads C (cuda_utilities.cpp:95-105), so "accumulate = 0"
+ *   (C := A*B) is the drop-in behaviour; accumulate = 1 gives a strict C += A*B.
+ *   C rows come back in BLOCKED row order (row_part order), exactly like
+ *   VBR::multiply (src/general/vbr.cpp:355).
+ *
+ * Every function returns 0 on success and a nonzero code otherwise;
+ * sparta_last_error() returns a description for the calling thread.  There is
+ * no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SPARTA_B200_H
+#define SPARTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPARTA_ABI_VERSION 1
+
+/* operand precision of the tensor-core path; accumulation is always fp32 */
+enum { SPARTA_BF16 = 0, SPARTA_FP16 = 1, SPARTA_TF32 = 2 };
+/* dense operand layouts (0 = the handle type's default) */
+enum { SPARTA_LAYOUT_DEFAULT = 0, SPARTA_COL_MAJOR = 1, SPARTA_ROW_MAJOR = 2 };
+/* status codes */
+enum {
+  SPARTA_OK = 0,
+  SPARTA_ERR_INVALID = 1,   /* bad argument */
+  SPARTA_ERR_CUDA = 2,      /* CUDA runtime / driver failure (message has the cause) */
+  SPARTA_ERR_NO_DEVICE = 3, /* no sm_100 device visible */
+  SPARTA_ERR_STATE = 4      /* call order violated (e.g. run before set_B) */
+};
+
+typedef struct sparta_handle sparta_handle;
+
+/* Tunables.  Zero-initialise and set struct_size = sizeof(sparta_options);
+ * every field left 0 takes its default. */
+typedef struct sparta_options {
+  int32_t struct_size;
+  int32_t precision;     /* SPARTA_BF16 (default) | SPARTA_FP16 | SPARTA_TF32 */
+  int32_t device;        /* 1 + CUDA device ordinal; 0 = the current device */
+  int32_t b_layout;      /* default: COL_MAJOR for VBR handles, ROW_MAJOR for BELLPACK/CSR */
+  int32_t c_layout;      /* same default as b_layout */
+  int32_t accumulate;    /* 0: C := A*B (default) ; 1: C += A*B */
+  int32_t seg_rows;      /* max rows per MMA segment, multiple of 16 <= 256 (default 64) */
+  int32_t acc_cols;      /* TMEM columns per accumulator stage: 256 (default) or 512 */
+  int32_t panel_stages;  /* smem pipeline depth, 2..8 (default 4) */
+  int32_t num_ctas;      /* persistent grid size (default: SM count) */
+  int64_t block_row_begin; /* shard: first block-row (default 0) */
+  int64_t block_row_end;   /* shard: one past the last block-row (default: all) */
+  int32_t reserved[8];
+} sparta_options;
+
+/* Statistics of a handle (all counts refer to the handle's shard). */
+typedef struct sparta_stats {
+  int64_t rows;            /* C rows of the shard */
+  int64_t cols;            /* A columns = B rows */
+  int64_t block_rows;      /* block-rows in the shard */
+  int64_t nz_blocks;       /* nonzero blocks */
+  int64_t nztot;           /* sum h*w over nonzero blocks (VBR::nztot, vbr.cpp:232) */
+  int64_t segments, super_rows, chunks, items;
+  int64_t a_packed_bytes;  /* device bytes of the packed A images */
+  int64_t b_bytes;         /* device bytes of the converted B operand */
+  int64_t c_bytes;         /* device bytes of C */
+  int32_t grid;            /* CTAs launched by sparta_run */
+  int32_t smem_bytes;      /* dynamic shared memory per CTA */
+  double  sched_imbalance; /* modelled max/mean CTA load */
+  double  upload_ms;       /* host->device + packing time of the last create/set_B */
+  int64_t kernel_launches; /* sm_100a SpMM launches issued through this handle */
+} sparta_stats;
+
+const char* sparta_last_error(void);
+int sparta_abi_version(void);
+/* number of visible CUDA devices with compute capability 10.x (0 on a CPU box) */
+int sparta_device_count(void);
+
+/* ---- handle API: device state persists across warm-up and repetitions ---- */
+
+/* A in the reference's VBR layout (struct VBR, include/matrices.h:93-122):
+ * row_part[block_rows+1], nzcount[block_rows], jab[sum nzcount] ascending per
+ * block-row, mab = nonzero blocks back to back, each column-major with ld = h.
+ * Host arrays are read during the call and never retained.
+ * Replaces the upload half of cublas_fixed_blocks_multiply (cuda_utilities.cpp:91-124). */
+int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                      int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                      const int64_t* jab, const float* mab, const sparta_options* opt);
+
+/* A as the Blocked-ELL bundle produced by prepare_cusparse_BLOCKEDELLPACK
+ * (cuda_utilities.cpp:1656-1710): ellColInd[ellColInd_rows*ellColInd_cols] with -1
+ * padding, ellValues row-major rows x (ellColInd_cols*ell_blocksize).
+ * Replaces the upload half of cusparse_gemm_custom_ellpack (:1497-1653) and
+ * compute_cutlass_bellpack (cutlass_bellpack_lib.cu:61-242). */
+int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols,
+                           int64_t ell_blocksize, int64_t ellColInd_rows,
+                           int64_t ellColInd_cols, const int64_t* ellColInd,
+                           const float* ellValues, const sparta_options* opt);
+
+/* Dense operand B (cols x n fp32).  ld: leading dimension in elements (>= cols for
+ * COL_MAJOR, >= n for ROW_MAJOR).  on_device != 0: B is a device pointer on the
+ * handle's device (e.g. the target of an NCCL broadcast). */
+int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device);
+
+/* Optional: initial C for accumulate = 1 (same layout/ld rules as sparta_get_C). */
+int sparta_set_C(sparta_handle* h, const float* C, int64_t ld, int on_device);
+
+/* One multiply on the handle's stream.  *dt_ms (may be NULL) = CUDA-event time
+ * around the compute kernel only, like the reference's dt (cuda_utilities.cpp:139,186-189). */
+int sparta_run(sparta_handle* h, float* dt_ms);
+/* Enqueue without timing or synchronisation (for CUDA-graph / external event timing). */
+int sparta_run_async(sparta_handle* h);
+int sparta_synchronize(sparta_handle* h);
+
+/* Copy the result (rows x n fp32) out.  on_device != 0: C is a device pointer. */
+int sparta_get_C(sparta_handle* h, float* C, int64_t ld, int on_device);
+
+/* Raw device views for zero-copy consumers (valid until the next set_B / destroy). */
+void* sparta_C_device_ptr(sparta_handle* h);
+int64_t sparta_C_device_ld(sparta_handle* h);
+/* the CUDA stream (cudaStream_t) the handle launches on */
+void* sparta_stream(sparta_handle* h);
+
+int sparta_get_stats(sparta_handle* h, sparta_stats* out);
+int sparta_destroy(sparta_handle* h);
+
+/* ---- one-shot calls with the reference's data flow (host in, host out) ---- */
+
+/* Replaces cublas_fixed_blocks_multiply (cuda_utilities.cpp:39-209, -M 4),
+ * cublas_blockmat_batched (:723-887, -M 7) and the undefined
+ * cublas_blockmat_multiplyAB (include/cuda_utilities.h:44): upload, multiply,
+ * download.  B column-major ld = ldb, C column-major ld = ldc. */
+int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                    const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
+                    const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
+                    int64_t ldc, int precision, float* dt_ms);
+
+/* Replaces cusparse_gemm_custom_ellpack (-M 3) / compute_cutlass_bellpack (-M 8).
+ * B and C row-major (cuda_utilities.cpp:1581-1591). */
+int sparta_bellpack_spmm(int64_t rows, int64_t cols, int64_t ell_blocksize,
+                         int64_t ellColInd_rows, int64_t ellColInd_cols,
+                         const int64_t* ellColInd, const float* ellValues, const float* B,
+                         int64_t ldb, int64_t n, float* C, int64_t ldc, int precision,
+                         float* dt_ms);
+
+/* ---- host-side helpers (no GPU needed) ---- */
+
+/* Contiguous block-row ranges balanced on nonzero-block area; cuts[parts+1]. */
+int sparta_partition_block_rows(int64_t block_rows, const int64_t* row_part,
+                                const int64_t* nzcount, int32_t parts, int64_t* cuts);
+
+/* ---- host-side format builders (no GPU needed; bit-exact with the reference) ---- */
+
+/* get_permutation / get_partition (src/general/utilities.cpp:8-43).  perm[n]; part needs
+ * n+1 slots, *part_len receives block_rows+1. */
+int sparta_host_permutation(int64_t n, const int64_t* grouping, int64_t* perm);
+int sparta_host_partition(int64_t n, const int64_t* grouping, int64_t* part, int64_t* part_len);
+
+/* VBR::fill_from_CSR_inplace (src/general/vbr.cpp:135-237) in linear time on a flat CSR
+ * (rowptr[rows+1], colind, val; val may be NULL when pattern_only).  The result is owned by
+ * the returned object; sparta_host_vbr_get exposes its arrays (valid until _free).
+ * dims[6] = rows, cols, block_rows, block_cols, block_col_size, nztot. */
+typedef struct sparta_host_vbr sparta_host_vbr;
+int sparta_host_vbr_fill(sparta_host_vbr** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                         const int64_t* colind, const float* val, int32_t pattern_only,
+                         const int64_t* grouping, int64_t block_col_size, int64_t row_block_size,
+                         int32_t force_fixed_size, int32_t threads);
+int sparta_host_vbr_get(sparta_host_vbr* v, int64_t* dims, const int64_t** row_part,
+                        const int64_t** nzcount, const int64_t** jab, const float** mab);
+int sparta_host_vbr_free(sparta_host_vbr* v);
+
+/* prepare_cusparse_BLOCKEDELLPACK (src/cuda/cuda_utilities.cpp:1656-1710).
+ * dims[3] = ell_blocksize, ellColInd_rows, ellColInd_cols. */
+typedef struct sparta_host_bell sparta_host_bell;
+int sparta_host_bellpack_from_vbr(sparta_host_bell** out, int64_t rows, int64_t cols,
+                                  int64_t block_col_size, const int64_t* nzcount,
+                                  const int64_t* jab, const float* mab, int32_t threads);
+int sparta_host_bellpack_get(sparta_host_bell* b, int64_t* dims, const int64_t** ellColInd,
+                             const float** ellValues);
+int sparta_host_bellpack_free(sparta_host_bell* b);
+
+/* Host-only access to the schedule itself so the CPU test-suite can interpret it
+ * (tests/sched_interp.py) without a GPU.  No arithmetic on matrix values happens
+ * in the library on this path.  `which`: 0 segments, 1 super-rows, 2 chunks,
+ * 3 items, 4 cta_ptr, 5 cta_items, 6 pack jobs (record layouts: csrc/sched_types.h).
+ * *data points into the plan and stays valid until sparta_plan_destroy. */
+typedef struct sparta_plan sparta_plan;
+int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_t block_rows,
+                           int64_t block_col_size, const int64_t* row_part,
+                           const int64_t* nzcount, const int64_t* jab, int64_t n,
+                           const sparta_options* opt);
+int sparta_plan_array(sparta_plan* plan, int32_t which, const void** data, int64_t* count,
+                      int32_t* record_bytes);
+int sparta_plan_stats(sparta_plan* plan, sparta_stats* out);
+int sparta_plan_destroy(sparta_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARTA_B200_H */

@@ -1,0 +1,713 @@
+// extern "C" boundary of libsparta_b200 (include/sparta_b200.h).
+//
+// Host-side responsibilities mirror what each reference multiply routine does
+// around its GEMM loop (src/cuda/cuda_utilities.cpp:91-105, 199-208): allocate,
+// upload A and B, time the compute with CUDA events, download C.  Here the
+// device state lives in a handle so warm-up and repetitions reuse it.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sparta_b200.h"
+#include "host_formats.h"
+#include "pack_kernels.h"
+#include "schedule.h"
+#include "spmm_kernel.h"
+
+using namespace sparta;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+static int fail_cuda(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return SPARTA_ERR_CUDA;
+}
+#define CU_TRY(call)                                        \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return fail_cuda(e_, #call);     \
+  } while (0)
+
+struct sparta_host_vbr { HostVBR v; };
+struct sparta_host_bell { HostBell b; };
+
+struct sparta_plan {
+  Structure st;
+  Assignment as;
+  ScheduleOptions sopt;
+  int64_t cols = 0, block_rows = 0, n = 0;
+  int panel_stages = 4, a_ring_bytes = 0;
+};
+
+struct sparta_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ScheduleOptions sopt;
+  int b_row_major = 0, c_row_major = 0, accumulate = 0;
+  int panel_stages = 4, a_ring_bytes = 0;
+  int64_t cols = 0, block_rows = 0, w = 0;
+  Structure st;   // jobs are dropped after packing
+  Assignment as;
+  Segment* d_segs = nullptr;
+  SuperRow* d_srows = nullptr;
+  Chunk* d_chunks = nullptr;
+  uint8_t* d_a = nullptr;
+  Item* d_items = nullptr;
+  int32_t* d_cta_ptr = nullptr;
+  int32_t* d_cta_items = nullptr;
+  void* d_B = nullptr;
+  size_t b_cap = 0;
+  int64_t ldk = 0, n = 0;
+  float* d_C = nullptr;
+  size_t c_cap = 0;
+  int64_t ldc = 0;
+  double upload_ms = 0;
+  int64_t launches = 0;
+};
+
+static void resolve_options(const sparta_options* in, sparta_options* o) {
+  memset(o, 0, sizeof(*o));
+  if (in) {
+    size_t sz = in->struct_size > 0 ? static_cast<size_t>(in->struct_size) : sizeof(*o);
+    memcpy(o, in, std::min(sz, sizeof(*o)));
+  }
+  if (o->seg_rows == 0) o->seg_rows = 64;
+  if (o->acc_cols == 0) o->acc_cols = 256;
+  if (o->panel_stages == 0) o->panel_stages = 4;
+}
+
+static int ring_bytes_for(int panel_stages) {
+  int b = kSmemMax - 1024 - kSmemCtrlBytes - panel_stages * kPanelBytes;
+  return b / 1024 * 1024;
+}
+
+// ---- BlockRows builders (format adapters) ---------------------------------
+
+static const char* blockrows_from_vbr(int64_t block_rows, int64_t w, const int64_t* row_part,
+                                      const int64_t* nzcount, const int64_t* jab, int64_t lo,
+                                      int64_t hi, BlockRows* br, int64_t* src_lo,
+                                      int64_t* src_hi) {
+  if (lo < 0 || hi > block_rows || lo > hi) return "block-row range out of bounds";
+  br->w = w;
+  int64_t jab_off = 0, mab_off = 0;
+  for (int64_t b = 0; b < lo; ++b) {
+    const int64_t H = row_part[b + 1] - row_part[b];
+    if (H < 0 || nzcount[b] < 0) return "row_part must be non-decreasing and nzcount non-negative";
+    jab_off += nzcount[b];
+    mab_off += nzcount[b] * H * w;
+  }
+  *src_lo = mab_off;
+  br->ptr.push_back(0);
+  for (int64_t b = lo; b < hi; ++b) {
+    const int64_t H = row_part[b + 1] - row_part[b];
+    if (H < 0 || nzcount[b] < 0) return "row_part must be non-decreasing and nzcount non-negative";
+    br->row0.push_back(row_part[b] - row_part[lo]);
+    br->height.push_back(H);
+    br->rs.push_back(1);   // blocks are column-major with ld = H (vbr.cpp:224)
+    br->ks.push_back(H);
+    for (int64_t q = 0; q < nzcount[b]; ++q) {
+      const int64_t jb = jab[jab_off + q];
+      if (q > 0 && jb <= jab[jab_off + q - 1]) return "jab must be strictly ascending inside a block-row";
+      if (jb < 0) return "negative column-block index";
+      br->col.push_back(jb);
+      br->src.push_back(mab_off - *src_lo + q * H * w);
+    }
+    br->ptr.push_back(static_cast<int64_t>(br->col.size()));
+    jab_off += nzcount[b];
+    mab_off += nzcount[b] * H * w;
+  }
+  *src_hi = mab_off;
+  return "";
+}
+
+static const char* blockrows_from_bell(int64_t bs, int64_t ind_rows, int64_t ind_cols,
+                                       const int64_t* ind, int64_t lo, int64_t hi, BlockRows* br,
+                                       int64_t* src_lo, int64_t* src_hi) {
+  if (lo < 0 || hi > ind_rows || lo > hi) return "block-row range out of bounds";
+  br->w = bs;
+  const int64_t val_cols = ind_cols * bs;  // ellValue_cols (cuda_utilities.cpp:1681)
+  *src_lo = lo * bs * val_cols;
+  *src_hi = hi * bs * val_cols;
+  br->ptr.push_back(0);
+  std::vector<std::pair<int64_t, int64_t>> row;
+  for (int64_t i = lo; i < hi; ++i) {
+    br->row0.push_back((i - lo) * bs);
+    br->height.push_back(bs);
+    br->rs.push_back(val_cols);  // values are row-major rows x ellValue_cols (:1699-1707)
+    br->ks.push_back(1);
+    row.clear();
+    for (int64_t s = 0; s < ind_cols; ++s) {
+      const int64_t jb = ind[i * ind_cols + s];
+      if (jb < 0) continue;  // -1 = padding block (:1693)
+      row.emplace_back(jb, (i - lo) * bs * val_cols + s * bs);
+    }
+    std::sort(row.begin(), row.end());
+    for (size_t t = 0; t < row.size(); ++t) {
+      if (t > 0 && row[t].first == row[t - 1].first) return "duplicate column block in an ELL row";
+      br->col.push_back(row[t].first);
+      br->src.push_back(row[t].second);
+    }
+    br->ptr.push_back(static_cast<int64_t>(br->col.size()));
+  }
+  return "";
+}
+
+// ---- handle construction ---------------------------------------------------
+
+static void free_handle(sparta_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_segs); cudaFree(h->d_srows); cudaFree(h->d_chunks); cudaFree(h->d_a);
+  cudaFree(h->d_items); cudaFree(h->d_cta_ptr); cudaFree(h->d_cta_items);
+  cudaFree(h->d_B); cudaFree(h->d_C);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+template <class T>
+static cudaError_t upload_vec(const std::vector<T>& v, T** dptr, cudaStream_t s) {
+  *dptr = nullptr;
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), bytes);
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  return e;
+}
+
+static int create_common(sparta_handle** out, BlockRows& br, const float* src_host,
+                         int64_t src_elems, int64_t cols, const sparta_options& o,
+                         int default_row_major) {
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SPARTA_ERR_NO_DEVICE, "no CUDA device visible (libsparta_b200 has no CPU path)");
+  }
+  int dev = 0;
+  if (o.device > 0) dev = o.device - 1; else CU_TRY(cudaGetDevice(&dev));
+  CU_TRY(cudaSetDevice(dev));
+  int major = 0, sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10)
+    return fail(SPARTA_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)");
+
+  sparta_handle* h = new sparta_handle();
+  h->device = dev;
+  h->sopt.precision = o.precision;
+  h->sopt.seg_rows = o.seg_rows;
+  h->sopt.acc_cols = o.acc_cols;
+  h->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : sms;
+  h->panel_stages = o.panel_stages;
+  h->a_ring_bytes = ring_bytes_for(o.panel_stages);
+  h->accumulate = o.accumulate ? 1 : 0;
+  h->b_row_major = o.b_layout == SPARTA_LAYOUT_DEFAULT ? default_row_major : (o.b_layout == SPARTA_ROW_MAJOR);
+  h->c_row_major = o.c_layout == SPARTA_LAYOUT_DEFAULT ? default_row_major : (o.c_layout == SPARTA_ROW_MAJOR);
+  h->cols = cols;
+  h->w = br.w;
+  h->block_rows = br.count();
+  if (o.precision < 0 || o.precision > 2 || o.panel_stages < 2 || o.panel_stages > kMaxPanelStages) {
+    delete h;
+    return fail(SPARTA_ERR_INVALID, "invalid precision or panel_stages");
+  }
+  const char* serr = build_structure(br, h->sopt, &h->st);
+  if (*serr) { delete h; return fail(SPARTA_ERR_INVALID, serr); }
+  if (static_cast<int64_t>(h->st.max_chunk_bytes) > h->a_ring_bytes) {
+    delete h;
+    return fail(SPARTA_ERR_INVALID, "a chunk's A images exceed the shared-memory ring; lower acc_cols or panel_stages");
+  }
+
+#define H_TRY(call)                                                            \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) { free_handle(h); return fail_cuda(e_, #call); }    \
+  } while (0)
+
+  H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  H_TRY(cudaEventCreate(&h->ev0));
+  H_TRY(cudaEventCreate(&h->ev1));
+  cudaEvent_t t0, t1;
+  H_TRY(cudaEventCreate(&t0));
+  H_TRY(cudaEventCreate(&t1));
+  H_TRY(cudaEventRecord(t0, h->stream));
+
+  H_TRY(upload_vec(h->st.segs, &h->d_segs, h->stream));
+  H_TRY(upload_vec(h->st.srows, &h->d_srows, h->stream));
+  H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
+  H_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_a), std::max<uint64_t>(h->st.a_bytes, 16)));
+
+  if (!h->st.jobs.empty()) {
+    // Stage the fp32 source on the device, pack it into MMA-ready images there.
+    float* d_src = nullptr;
+    PackJob* d_jobs = nullptr;
+    H_TRY(cudaMalloc(reinterpret_cast<void**>(&d_src), std::max<int64_t>(src_elems, 1) * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(d_src, src_host, src_elems * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = upload_vec(h->st.jobs, &d_jobs, h->stream);
+    if (e == cudaSuccess)
+      e = pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_src);
+    cudaFree(d_jobs);
+    if (e != cudaSuccess) { free_handle(h); return fail_cuda(e, "A upload / pack"); }
+  }
+  std::vector<PackJob>().swap(h->st.jobs);
+  H_TRY(cudaEventRecord(t1, h->stream));
+  H_TRY(cudaEventSynchronize(t1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  h->upload_ms = ms;
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+#undef H_TRY
+  *out = h;
+  return SPARTA_OK;
+}
+
+// ---- extern "C" ------------------------------------------------------------
+
+extern "C" {
+
+const char* sparta_last_error(void) { return g_last_error.c_str(); }
+int sparta_abi_version(void) { return SPARTA_ABI_VERSION; }
+
+int sparta_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                      int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                      const int64_t* jab, const float* mab, const sparta_options* opt) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows < 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part || (block_rows && !nzcount))
+    return fail(SPARTA_ERR_INVALID, "invalid VBR dimensions or NULL index arrays");
+  if (block_rows > 0 && row_part[block_rows] != rows)
+    return fail(SPARTA_ERR_INVALID, "row_part[block_rows] must equal rows (VBR::partition_check)");
+  sparta_options o;
+  resolve_options(opt, &o);
+  const int64_t lo = o.block_row_begin;
+  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : block_rows;
+  BlockRows br;
+  int64_t src_lo = 0, src_hi = 0;
+  const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, lo, hi, &br, &src_lo, &src_hi);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  const int64_t bc = (cols - 1) / block_col_size + 1;
+  for (int64_t jb : br.col)
+    if (jb >= bc) return fail(SPARTA_ERR_INVALID, "jab entry beyond the last column block");
+  if (src_hi > src_lo && !mab) return fail(SPARTA_ERR_INVALID, "mab is NULL");
+  return create_common(out, br, mab ? mab + src_lo : nullptr, src_hi - src_lo, cols, o, 0);
+}
+
+int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t ell_blocksize,
+                           int64_t ellColInd_rows, int64_t ellColInd_cols,
+                           const int64_t* ellColInd, const float* ellValues,
+                           const sparta_options* opt) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (ell_blocksize <= 0 || rows < 0 || cols <= 0 || ellColInd_rows < 0 || ellColInd_cols < 0)
+    return fail(SPARTA_ERR_INVALID, "invalid Blocked-ELL dimensions");
+  // same shape rule as prepare_cusparse_BLOCKEDELLPACK (cuda_utilities.cpp:1664-1670)
+  if (rows % ell_blocksize || cols % ell_blocksize || ellColInd_rows != rows / ell_blocksize)
+    return fail(SPARTA_ERR_INVALID, "rows and cols must be multiples of ell_blocksize");
+  if (ellColInd_rows * ellColInd_cols > 0 && (!ellColInd || !ellValues))
+    return fail(SPARTA_ERR_INVALID, "NULL Blocked-ELL arrays");
+  sparta_options o;
+  resolve_options(opt, &o);
+  const int64_t lo = o.block_row_begin;
+  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : ellColInd_rows;
+  BlockRows br;
+  int64_t src_lo = 0, src_hi = 0;
+  const char* e = blockrows_from_bell(ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd, lo, hi, &br, &src_lo, &src_hi);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  for (int64_t jb : br.col)
+    if (jb >= cols / ell_blocksize) return fail(SPARTA_ERR_INVALID, "ellColInd entry beyond the last column block");
+  return create_common(out, br, ellValues ? ellValues + src_lo : nullptr, src_hi - src_lo, cols, o, 1);
+}
+
+int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device) {
+  if (!h || !B) return fail(SPARTA_ERR_INVALID, "NULL handle or B");
+  if (n <= 0) return fail(SPARTA_ERR_INVALID, "n must be positive");
+  const int64_t min_ld = h->b_row_major ? n : h->cols;
+  if (ld < min_ld) return fail(SPARTA_ERR_INVALID, "leading dimension of B too small");
+  CU_TRY(cudaSetDevice(h->device));
+  cudaEvent_t t0, t1;
+  CU_TRY(cudaEventCreate(&t0));
+  CU_TRY(cudaEventCreate(&t1));
+  CU_TRY(cudaEventRecord(t0, h->stream));
+  const int esize = prec_esize(h->sopt.precision);
+  const int64_t ldk = (h->cols + 63) / 64 * 64;
+  const size_t b_bytes = static_cast<size_t>(n) * ldk * esize;
+  if (b_bytes > h->b_cap) {
+    cudaFree(h->d_B);
+    h->d_B = nullptr; h->b_cap = 0;
+    CU_TRY(cudaMalloc(&h->d_B, b_bytes));
+    h->b_cap = b_bytes;
+  }
+  h->ldk = ldk;
+  // fp32 staging copy (host sources only)
+  const float* src = B;
+  float* d_stage = nullptr;
+  int64_t src_ld = ld;
+  if (!on_device) {
+    const int64_t lines = h->b_row_major ? h->cols : n;     // number of ld-strided lines
+    const int64_t width = h->b_row_major ? n : h->cols;     // contiguous elements per line
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&d_stage), static_cast<size_t>(lines) * width * sizeof(float)));
+    cudaError_t e = cudaMemcpy2DAsync(d_stage, width * sizeof(float), B, ld * sizeof(float),
+                                      width * sizeof(float), lines, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { cudaFree(d_stage); return fail_cuda(e, "B upload"); }
+    src = d_stage;
+    src_ld = width;
+  }
+  cudaError_t e = convert_b(src, src_ld, h->b_row_major, h->d_B, ldk, h->cols, n, h->sopt.precision, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_stage);
+  if (e != cudaSuccess) return fail_cuda(e, "B conversion");
+
+  if (n != h->n) {
+    const char* serr = build_assignment(h->st, h->sopt, n, &h->as);
+    if (*serr) return fail(SPARTA_ERR_INVALID, serr);
+    cudaFree(h->d_items); cudaFree(h->d_cta_ptr); cudaFree(h->d_cta_items);
+    h->d_items = nullptr; h->d_cta_ptr = nullptr; h->d_cta_items = nullptr;
+    CU_TRY(upload_vec(h->as.items, &h->d_items, h->stream));
+    CU_TRY(upload_vec(h->as.cta_ptr, &h->d_cta_ptr, h->stream));
+    CU_TRY(upload_vec(h->as.cta_items, &h->d_cta_items, h->stream));
+    // C: column-major ld padded to 4 rows so the epilogue can use 16-byte stores
+    h->ldc = h->c_row_major ? n : (h->st.rows + 3) / 4 * 4;
+    const size_t c_elems = h->c_row_major ? static_cast<size_t>(h->st.rows) * n : static_cast<size_t>(h->ldc) * n;
+    const size_t c_bytes = std::max<size_t>(c_elems, 4) * sizeof(float);
+    if (c_bytes > h->c_cap) {
+      cudaFree(h->d_C);
+      h->d_C = nullptr; h->c_cap = 0;
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_C), c_bytes));
+      h->c_cap = c_bytes;
+    }
+    CU_TRY(cudaMemsetAsync(h->d_C, 0, c_bytes, h->stream));
+    h->n = n;
+  }
+  CU_TRY(cudaEventRecord(t1, h->stream));
+  CU_TRY(cudaEventSynchronize(t1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  h->upload_ms = ms;
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return SPARTA_OK;
+}
+
+static int copy_c(sparta_handle* h, float* C, int64_t ld, int on_device, bool to_handle) {
+  if (!h || !C) return fail(SPARTA_ERR_INVALID, "NULL handle or C");
+  if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called first");
+  const int64_t rows = h->st.rows;
+  const int64_t lines = h->c_row_major ? rows : h->n;
+  const int64_t width = h->c_row_major ? h->n : rows;
+  if (ld < width) return fail(SPARTA_ERR_INVALID, "leading dimension of C too small");
+  if (lines == 0 || width == 0) return SPARTA_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice
+                              : (to_handle ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+  if (to_handle)
+    CU_TRY(cudaMemcpy2DAsync(h->d_C, h->ldc * sizeof(float), C, ld * sizeof(float), width * sizeof(float), lines, kind, h->stream));
+  else
+    CU_TRY(cudaMemcpy2DAsync(C, ld * sizeof(float), h->d_C, h->ldc * sizeof(float), width * sizeof(float), lines, kind, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return SPARTA_OK;
+}
+
+int sparta_set_C(sparta_handle* h, const float* C, int64_t ld, int on_device) {
+  return copy_c(h, const_cast<float*>(C), ld, on_device, true);
+}
+int sparta_get_C(sparta_handle* h, float* C, int64_t ld, int on_device) {
+  return copy_c(h, C, ld, on_device, false);
+}
+
+static int launch(sparta_handle* h) {
+  if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");
+  if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called before run");
+  CU_TRY(cudaSetDevice(h->device));
+  if (h->as.grid == 0) return SPARTA_OK;  // empty shard: nothing to compute
+  SpmmParams p;
+  memset(&p, 0, sizeof(p));
+  p.items = h->d_items; p.cta_ptr = h->d_cta_ptr; p.cta_items = h->d_cta_items;
+  p.srows = h->d_srows; p.segs = h->d_segs; p.chunks = h->d_chunks; p.a_packed = h->d_a;
+  p.C = h->d_C;
+  p.c_sr = h->c_row_major ? h->ldc : 1;
+  p.c_sj = h->c_row_major ? 1 : h->ldc;
+  p.n = static_cast<int32_t>(h->n);
+  p.accumulate = h->accumulate;
+  // tcgen05 instruction descriptor (kind::f16 / kind::tf32): D fp32 at [4,6), A/B
+  // format at [7,10)/[10,13) (0 f16, 1 bf16, 2 tf32), both K-major, M=128 at [24,29)
+  const uint32_t fmt = h->sopt.precision == PREC_BF16 ? 1u : (h->sopt.precision == PREC_FP16 ? 0u : 2u);
+  p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
+  p.kind_tf32 = h->sopt.precision == PREC_TF32;
+  p.panel_stages = h->panel_stages;
+  p.a_ring_bytes = h->a_ring_bytes;
+  p.acc_stages = 512 / h->sopt.acc_cols;
+  p.acc_stage_cols = h->sopt.acc_cols;
+  const char* err = "";
+  cudaError_t e = spmm_launch(p, h->d_B, h->cols, h->ldk, h->sopt.precision, h->as.grid, h->stream, &err);
+  if (e != cudaSuccess) return fail_cuda(e, err);
+  ++h->launches;
+  return SPARTA_OK;
+}
+
+int sparta_run_async(sparta_handle* h) { return launch(h); }
+
+int sparta_synchronize(sparta_handle* h) {
+  if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return SPARTA_OK;
+}
+
+int sparta_run(sparta_handle* h, float* dt_ms) {
+  if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");
+  if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called before run");
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaEventRecord(h->ev0, h->stream));
+  const int rc = launch(h);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  CU_TRY(cudaEventSynchronize(h->ev1));
+  CU_TRY(cudaGetLastError());
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (dt_ms) *dt_ms = ms;
+  return SPARTA_OK;
+}
+
+void* sparta_C_device_ptr(sparta_handle* h) { return h ? h->d_C : nullptr; }
+int64_t sparta_C_device_ld(sparta_handle* h) { return h ? h->ldc : 0; }
+void* sparta_stream(sparta_handle* h) { return h ? h->stream : nullptr; }
+
+static void fill_stats(const Structure& st, const Assignment& as, int64_t cols, int64_t block_rows,
+                       int panel_stages, int a_ring_bytes, sparta_stats* s) {
+  memset(s, 0, sizeof(*s));
+  s->rows = st.rows; s->cols = cols; s->block_rows = block_rows;
+  s->nz_blocks = st.n_blocks; s->nztot = st.nztot;
+  s->segments = static_cast<int64_t>(st.segs.size());
+  s->super_rows = static_cast<int64_t>(st.srows.size());
+  s->chunks = static_cast<int64_t>(st.chunks.size());
+  s->items = static_cast<int64_t>(as.items.size());
+  s->a_packed_bytes = static_cast<int64_t>(st.a_bytes);
+  s->grid = as.grid;
+  s->smem_bytes = spmm_smem_bytes(panel_stages, a_ring_bytes);
+  s->sched_imbalance = as.mean_cta_cost > 0 ? as.max_cta_cost / as.mean_cta_cost : 1.0;
+}
+
+int sparta_get_stats(sparta_handle* h, sparta_stats* out) {
+  if (!h || !out) return fail(SPARTA_ERR_INVALID, "NULL handle or stats");
+  fill_stats(h->st, h->as, h->cols, h->block_rows, h->panel_stages, h->a_ring_bytes, out);
+  out->b_bytes = static_cast<int64_t>(h->n) * h->ldk * prec_esize(h->sopt.precision);
+  out->c_bytes = h->c_row_major ? h->st.rows * h->n * 4 : h->ldc * h->n * 4;
+  out->upload_ms = h->upload_ms;
+  out->kernel_launches = h->launches;
+  return SPARTA_OK;
+}
+
+int sparta_destroy(sparta_handle* h) {
+  free_handle(h);
+  return SPARTA_OK;
+}
+
+int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                    const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
+                    const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
+                    int64_t ldc, int precision, float* dt_ms) {
+  sparta_options o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  o.precision = precision;
+  sparta_handle* h = nullptr;
+  int rc = sparta_vbr_create(&h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o);
+  if (rc) return rc;
+  rc = sparta_set_B(h, B, ldb, n, 0);
+  if (!rc) rc = sparta_run(h, dt_ms);
+  if (!rc) rc = sparta_get_C(h, C, ldc, 0);
+  const std::string keep = g_last_error;
+  sparta_destroy(h);
+  if (rc) g_last_error = keep;
+  return rc;
+}
+
+int sparta_bellpack_spmm(int64_t rows, int64_t cols, int64_t ell_blocksize,
+                         int64_t ellColInd_rows, int64_t ellColInd_cols,
+                         const int64_t* ellColInd, const float* ellValues, const float* B,
+                         int64_t ldb, int64_t n, float* C, int64_t ldc, int precision,
+                         float* dt_ms) {
+  sparta_options o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  o.precision = precision;
+  sparta_handle* h = nullptr;
+  int rc = sparta_bellpack_create(&h, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd, ellValues, &o);
+  if (rc) return rc;
+  rc = sparta_set_B(h, B, ldb, n, 0);
+  if (!rc) rc = sparta_run(h, dt_ms);
+  if (!rc) rc = sparta_get_C(h, C, ldc, 0);
+  const std::string keep = g_last_error;
+  sparta_destroy(h);
+  if (rc) g_last_error = keep;
+  return rc;
+}
+
+int sparta_partition_block_rows(int64_t block_rows, const int64_t* row_part,
+                                const int64_t* nzcount, int32_t parts, int64_t* cuts) {
+  if (block_rows < 0 || parts <= 0 || !cuts || (block_rows && (!row_part || !nzcount)))
+    return fail(SPARTA_ERR_INVALID, "invalid partition request");
+  partition_block_rows(block_rows, row_part, nzcount, parts, cuts);
+  return SPARTA_OK;
+}
+
+int sparta_host_permutation(int64_t n, const int64_t* grouping, int64_t* perm) {
+  if (n < 0 || (n && (!grouping || !perm))) return fail(SPARTA_ERR_INVALID, "NULL grouping or perm");
+  host_permutation(grouping, n, perm);
+  return SPARTA_OK;
+}
+
+int sparta_host_partition(int64_t n, const int64_t* grouping, int64_t* part, int64_t* part_len) {
+  if (n < 0 || !part || !part_len || (n && !grouping)) return fail(SPARTA_ERR_INVALID, "NULL argument");
+  *part_len = host_partition(grouping, n, part);
+  return SPARTA_OK;
+}
+
+int sparta_host_vbr_fill(sparta_host_vbr** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                         const int64_t* colind, const float* val, int32_t pattern_only,
+                         const int64_t* grouping, int64_t block_col_size, int64_t row_block_size,
+                         int32_t force_fixed_size, int32_t threads) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows <= 0 || cols <= 0 || !rowptr || !grouping || (rowptr[rows] && !colind) ||
+      (!pattern_only && rowptr[rows] && !val))
+    return fail(SPARTA_ERR_INVALID, "invalid CSR input");
+  sparta_host_vbr* v = new sparta_host_vbr();
+  const char* e = host_vbr_fill(rows, cols, rowptr, colind, val, pattern_only != 0, grouping,
+                                block_col_size, row_block_size, force_fixed_size != 0,
+                                threads > 0 ? threads : 1, &v->v);
+  if (*e) { delete v; return fail(SPARTA_ERR_INVALID, e); }
+  *out = v;
+  return SPARTA_OK;
+}
+
+int sparta_host_vbr_get(sparta_host_vbr* v, int64_t* dims, const int64_t** row_part,
+                        const int64_t** nzcount, const int64_t** jab, const float** mab) {
+  if (!v || !dims) return fail(SPARTA_ERR_INVALID, "NULL argument");
+  dims[0] = v->v.rows; dims[1] = v->v.cols; dims[2] = v->v.block_rows; dims[3] = v->v.block_cols;
+  dims[4] = v->v.block_col_size; dims[5] = v->v.nztot;
+  if (row_part) *row_part = v->v.row_part.data();
+  if (nzcount) *nzcount = v->v.nzcount.data();
+  if (jab) *jab = v->v.jab.data();
+  if (mab) *mab = v->v.mab.data();
+  return SPARTA_OK;
+}
+
+int sparta_host_vbr_free(sparta_host_vbr* v) { delete v; return SPARTA_OK; }
+
+int sparta_host_bellpack_from_vbr(sparta_host_bell** out, int64_t rows, int64_t cols,
+                                  int64_t block_col_size, const int64_t* nzcount,
+                                  const int64_t* jab, const float* mab, int32_t threads) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!nzcount) return fail(SPARTA_ERR_INVALID, "NULL nzcount");
+  sparta_host_bell* b = new sparta_host_bell();
+  const char* e = host_bellpack_from_vbr(rows, cols, block_col_size, nzcount, jab, mab,
+                                         threads > 0 ? threads : 1, &b->b);
+  if (*e) { delete b; return fail(SPARTA_ERR_INVALID, e); }
+  *out = b;
+  return SPARTA_OK;
+}
+
+int sparta_host_bellpack_get(sparta_host_bell* b, int64_t* dims, const int64_t** ellColInd,
+                             const float** ellValues) {
+  if (!b || !dims) return fail(SPARTA_ERR_INVALID, "NULL argument");
+  dims[0] = b->b.blocksize; dims[1] = b->b.ind_rows; dims[2] = b->b.ind_cols;
+  if (ellColInd) *ellColInd = b->b.col_ind.data();
+  if (ellValues) *ellValues = b->b.values.data();
+  return SPARTA_OK;
+}
+
+int sparta_host_bellpack_free(sparta_host_bell* b) { delete b; return SPARTA_OK; }
+
+int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_t block_rows,
+                           int64_t block_col_size, const int64_t* row_part,
+                           const int64_t* nzcount, const int64_t* jab, int64_t n,
+                           const sparta_options* opt) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows < 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part)
+    return fail(SPARTA_ERR_INVALID, "invalid VBR dimensions");
+  sparta_options o;
+  resolve_options(opt, &o);
+  BlockRows br;
+  int64_t src_lo = 0, src_hi = 0;
+  const int64_t lo = o.block_row_begin;
+  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : block_rows;
+  const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, lo, hi, &br, &src_lo, &src_hi);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  sparta_plan* p = new sparta_plan();
+  p->sopt.precision = o.precision;
+  p->sopt.seg_rows = o.seg_rows;
+  p->sopt.acc_cols = o.acc_cols;
+  p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  p->cols = cols; p->block_rows = br.count(); p->n = n;
+  p->panel_stages = o.panel_stages;
+  p->a_ring_bytes = ring_bytes_for(o.panel_stages);
+  e = build_structure(br, p->sopt, &p->st);
+  if (!*e) e = build_assignment(p->st, p->sopt, n, &p->as);
+  if (*e) { delete p; return fail(SPARTA_ERR_INVALID, e); }
+  *out = p;
+  return SPARTA_OK;
+}
+
+int sparta_plan_array(sparta_plan* plan, int32_t which, const void** data, int64_t* count,
+                      int32_t* record_bytes) {
+  if (!plan || !data || !count || !record_bytes) return fail(SPARTA_ERR_INVALID, "NULL argument");
+#define PLAN_ARR(vec, T)                                   \
+  do {                                                     \
+    *data = (vec).data();                                  \
+    *count = static_cast<int64_t>((vec).size());           \
+    *record_bytes = static_cast<int32_t>(sizeof(T));       \
+    return SPARTA_OK;                                      \
+  } while (0)
+  switch (which) {
+    case 0: PLAN_ARR(plan->st.segs, Segment);
+    case 1: PLAN_ARR(plan->st.srows, SuperRow);
+    case 2: PLAN_ARR(plan->st.chunks, Chunk);
+    case 3: PLAN_ARR(plan->as.items, Item);
+    case 4: PLAN_ARR(plan->as.cta_ptr, int32_t);
+    case 5: PLAN_ARR(plan->as.cta_items, int32_t);
+    case 6: PLAN_ARR(plan->st.jobs, PackJob);
+  }
+#undef PLAN_ARR
+  return fail(SPARTA_ERR_INVALID, "unknown plan array id");
+}
+
+int sparta_plan_stats(sparta_plan* plan, sparta_stats* out) {
+  if (!plan || !out) return fail(SPARTA_ERR_INVALID, "NULL argument");
+  fill_stats(plan->st, plan->as, plan->cols, plan->block_rows, plan->panel_stages, plan->a_ring_bytes, out);
+  return SPARTA_OK;
+}
+
+int sparta_plan_destroy(sparta_plan* plan) {
+  delete plan;
+  return SPARTA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Host-side format builders of the product: grouping -> (permutation, partition) ->
+// VBR arrays -> Blocked-ELL bundle.  From-scratch, linear-time and multi-threaded,
+// but required to reproduce the reference's arrays bit for bit:
+//   get_permutation / get_partition   src/general/utilities.cpp:8-43
+//   VBR::fill_from_CSR_inplace        src/general/vbr.cpp:135-237  (O(nnz*block_cols) there)
+//   prepare_cusparse_BLOCKEDELLPACK   src/cuda/cuda_utilities.cpp:1656-1710
+#include "host_formats.h"
+
+#include <algorithm>
+#include <numeric>
+#include <thread>
+
+namespace sparta {
+
+// The reference orders rows with std::sort (unstable) keyed on the group id through a
+// comparator that takes `int` indices.  The order of rows inside a group is therefore
+// whatever libstdc++'s introsort produces; the only way to match it is to run the same
+// algorithm with a comparator that answers identically.
+void host_permutation(const int64_t* grouping, int64_t n, int64_t* perm) {
+  std::iota(perm, perm + n, static_cast<int64_t>(0));
+  std::sort(perm, perm + n, [grouping](int a, int b) { return grouping[a] < grouping[b]; });
+}
+
+int64_t host_partition(const int64_t* grouping, int64_t n, int64_t* part) {
+  std::vector<int64_t> g(grouping, grouping + n);
+  std::sort(g.begin(), g.end());
+  int64_t count = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (i == 0 || g[i] != g[i - 1]) part[count++] = i;
+  part[count++] = n;
+  return count;
+}
+
+template <class F>
+static void parallel_for(int64_t n, int threads, F fn) {
+  if (threads <= 1 || n < 2) {
+    fn(0, n);
+    return;
+  }
+  threads = static_cast<int>(std::min<int64_t>(threads, n));
+  std::vector<std::thread> pool;
+  const int64_t per = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    const int64_t lo = t * per, hi = std::min<int64_t>(n, lo + per);
+    if (lo >= hi) break;
+    pool.emplace_back([=] { fn(lo, hi); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+const char* host_vbr_fill(int64_t rows_in, int64_t cols_in, const int64_t* rowptr,
+                          const int64_t* colind, const float* val, bool pattern_only,
+                          const int64_t* grouping, int64_t w, int64_t row_block_size,
+                          bool force_fixed, int threads, HostVBR* out) {
+  if (w <= 0) return "column block size must be positive";
+  if (force_fixed && row_block_size <= 0) return "force_fixed needs a positive row block size";
+  std::vector<int64_t> perm(rows_in), part(rows_in + 1);
+  host_permutation(grouping, rows_in, perm.data());
+  part.resize(host_partition(grouping, rows_in, part.data()));
+
+  int64_t rows = rows_in, cols = cols_in;
+  if (force_fixed) {  // vbr.cpp:142-147: pad to whole blocks, the last block-row absorbs the padding rows
+    rows = ((rows_in - 1) / row_block_size + 1) * row_block_size;
+    cols = ((cols_in - 1) / w + 1) * w;
+    part.back() = rows;
+  }
+  const int64_t block_rows = static_cast<int64_t>(part.size()) - 1;
+  const int64_t block_cols = (cols - 1) / w + 1;
+  out->rows = rows; out->cols = cols; out->block_rows = block_rows; out->block_cols = block_cols;
+  out->block_col_size = w;
+  out->row_part = part;
+  out->nzcount.assign(block_rows, 0);
+
+  // pass 1: distinct column blocks per block-row (stamp array per thread)
+  std::vector<std::vector<int64_t>> row_jab(block_rows);
+  parallel_for(block_rows, threads, [&](int64_t lo, int64_t hi) {
+    std::vector<int64_t> stamp(block_cols, -1);
+    for (int64_t ib = lo; ib < hi; ++ib) {
+      std::vector<int64_t>& list = row_jab[ib];
+      for (int64_t r = part[ib]; r < part[ib + 1]; ++r) {
+        if (r >= rows_in) break;  // padding rows hold nothing
+        const int64_t i = perm[r];
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+          const int64_t jb = colind[p] / w;
+          if (stamp[jb] != ib) { stamp[jb] = ib; list.push_back(jb); }
+        }
+      }
+      std::sort(list.begin(), list.end());
+      out->nzcount[ib] = static_cast<int64_t>(list.size());
+    }
+  });
+
+  // offsets
+  std::vector<int64_t> jab_off(block_rows + 1, 0), mab_off(block_rows + 1, 0);
+  for (int64_t ib = 0; ib < block_rows; ++ib) {
+    const int64_t h = part[ib + 1] - part[ib];
+    jab_off[ib + 1] = jab_off[ib] + out->nzcount[ib];
+    mab_off[ib + 1] = mab_off[ib] + out->nzcount[ib] * h * w;
+  }
+  out->jab.resize(jab_off[block_rows]);
+  out->nztot = mab_off[block_rows];
+  out->mab.assign(static_cast<size_t>(out->nztot), 0.0f);
+
+  // pass 2: scatter values; block (ib, slot) is column-major with ld = h (vbr.cpp:224)
+  parallel_for(block_rows, threads, [&](int64_t lo, int64_t hi) {
+    std::vector<int64_t> slot(block_cols, 0);
+    for (int64_t ib = lo; ib < hi; ++ib) {
+      const std::vector<int64_t>& list = row_jab[ib];
+      std::copy(list.begin(), list.end(), out->jab.begin() + jab_off[ib]);
+      for (size_t s = 0; s < list.size(); ++s) slot[list[s]] = static_cast<int64_t>(s);
+      const int64_t h = part[ib + 1] - part[ib];
+      float* base = out->mab.data() + mab_off[ib];
+      for (int64_t r = part[ib]; r < part[ib + 1]; ++r) {
+        if (r >= rows_in) break;
+        const int64_t i = perm[r];
+        for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+          const int64_t j = colind[p];
+          base[slot[j / w] * w * h + h * (j % w) + (r - part[ib])] = pattern_only ? 1.0f : val[p];
+        }
+      }
+    }
+  });
+  return "";
+}
+
+const char* host_bellpack_from_vbr(int64_t rows, int64_t cols, int64_t bs, const int64_t* nzcount,
+                                   const int64_t* jab, const float* mab, int threads,
+                                   HostBell* out) {
+  if (bs <= 0 || rows % bs || cols % bs) return "rows and cols must be multiples of the block size";
+  const int64_t ind_rows = rows / bs;
+  int64_t width = 0;
+  for (int64_t i = 0; i < ind_rows; ++i) width = std::max(width, nzcount[i]);
+  out->blocksize = bs; out->ind_rows = ind_rows; out->ind_cols = width;
+  out->col_ind.assign(static_cast<size_t>(ind_rows * width), -1);   // -1 = padding block (:1693)
+  out->values.assign(static_cast<size_t>(rows * width * bs), 0.0f);
+  std::vector<int64_t> joff(ind_rows + 1, 0);
+  for (int64_t i = 0; i < ind_rows; ++i) joff[i + 1] = joff[i] + nzcount[i];
+  const int64_t val_cols = width * bs;
+  parallel_for(ind_rows, threads, [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      const float* blocks = mab + joff[i] * bs * bs;
+      for (int64_t s = 0; s < nzcount[i]; ++s) {
+        out->col_ind[i * width + s] = jab[joff[i] + s];
+        const float* blk = blocks + s * bs * bs;  // column-major bs x bs
+        for (int64_t k = 0; k < bs; ++k)
+          for (int64_t r = 0; r < bs; ++r)
+            out->values[(i * bs + r) * val_cols + s * bs + k] = blk[k * bs + r];
+      }
+    }
+  });
+  return "";
+}
+
+}  // namespace sparta

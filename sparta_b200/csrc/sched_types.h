@@ -1,0 +1,67 @@
+// Tile-schedule records shared by the host scheduler (schedule.cpp) and the
+// sm_100a SpMM kernel (spmm_kernel.cu).  All plain 32-bit PODs so they can be
+// memcpy'd to the device unchanged.
+//
+// Vocabulary (follows the reference's VBR terms, include/matrices.h:93-122):
+//   block-row  : one entry of VBR::row_part (variable height h)
+//   segment    : <= seg_rows consecutive rows of one block-row (MMA N operand)
+//   super-row  : a set of segments whose fp32 accumulators share one TMEM
+//                allocation; the unit a CTA owns for one column tile of B
+//   chunk      : one (column block, 128-byte K slab) of a super-row's merged
+//                column-block list; the unit of the smem pipeline
+#pragma once
+#include <stdint.h>
+
+namespace sparta {
+
+struct Segment {
+  int32_t c_row0;     // first row of C (blocked row order) this segment writes
+  int32_t h;          // true number of rows
+  int32_t h_pad;      // h rounded up to 16 (MMA N granularity at M=128)
+  int32_t tmem_col;   // first accumulator column inside the super-row
+};
+
+struct SuperRow {
+  int32_t seg_begin;    // into segs[]
+  int32_t seg_count;    // <= 32 (chunk mask width)
+  int32_t chunk_begin;  // into chunks[]
+  int32_t chunk_count;
+  int32_t n_cols;       // sum of h_pad (<= tmem columns per accumulator stage)
+  int32_t pad_[3];
+};
+
+struct Chunk {
+  int32_t  k0;        // first B row (k index) of this K slab
+  uint32_t mask;      // bit m set <=> member segment m has a block here
+  uint32_t a_off16;   // offset of the packed A images of this chunk, 16-byte units
+  uint32_t a_bytes;   // total bytes of those images (sum h_pad*128 over set bits)
+  int32_t  ksteps;    // MMA K steps to issue (1..4), covers the block's true width
+  int32_t  pad_[3];
+};
+
+struct Item {
+  int32_t srow;       // super-row id
+  int32_t j0;         // first column of B/C of this 128-wide column tile
+};
+
+// One packed A image = h_pad rows x 128 bytes in the K-major SWIZZLE_128B
+// canonical layout, i.e. the exact bytes the MMA reads from shared memory.
+struct PackJob {
+  int64_t src_base;   // element offset into the fp32 source (VBR mab / ELL values)
+  int64_t src_rs;     // element stride between consecutive rows of the block
+  int64_t src_ks;     // element stride between consecutive k of the block
+  int32_t h;          // valid rows
+  int32_t h_pad;
+  int32_t k_count;    // valid k in this slab (<= 128/esize)
+  uint32_t dst_off16; // destination offset, 16-byte units
+};
+
+enum Precision : int32_t { PREC_BF16 = 0, PREC_FP16 = 1, PREC_TF32 = 2 };
+
+static inline int prec_esize(int p) { return p == PREC_TF32 ? 4 : 2; }
+
+constexpr int kTileJ      = 128;     // MMA M = columns of B per tile
+constexpr int kPanelBytes = 16384;   // 128 rows x 128 bytes
+constexpr int kMaxMembers = 32;
+
+}  // namespace sparta

@@ -1,0 +1,62 @@
+// Host-side tile scheduler: turns the VBR / Blocked-ELL index arrays into the
+// work lists the sm_100a kernel walks.  Pure C++ (no CUDA) so it is testable on
+// a CPU-only box.
+#pragma once
+#include <stdint.h>
+#include <vector>
+#include "sched_types.h"
+
+namespace sparta {
+
+// Format-neutral view of the nonzero blocks of a range of block-rows.
+struct BlockRows {
+  int64_t w = 0;                  // column-block width (VBR::block_col_size)
+  std::vector<int64_t> row0;      // first C row of each block-row (relative to the shard)
+  std::vector<int64_t> height;    // rows in the block-row
+  std::vector<int64_t> ptr;       // [count+1] ranges into col/src
+  std::vector<int64_t> col;       // column-block index jb of each nonzero block
+  std::vector<int64_t> src;       // element offset of the block's (0,0) entry in the fp32 source
+  std::vector<int64_t> rs;        // per block-row: element stride between rows of a block
+  std::vector<int64_t> ks;        // per block-row: element stride between k of a block
+  int64_t count() const { return static_cast<int64_t>(height.size()); }
+};
+
+struct ScheduleOptions {
+  int precision = PREC_BF16;
+  int seg_rows = 64;       // max rows per segment (multiple of 16, <= 256)
+  int acc_cols = 256;      // TMEM columns per accumulator stage: 256 (2 stages) or 512 (1)
+  int num_ctas = 148;      // persistent grid size upper bound
+};
+
+struct Structure {           // independent of the number of B columns
+  std::vector<Segment>  segs;
+  std::vector<SuperRow> srows;
+  std::vector<Chunk>    chunks;
+  std::vector<PackJob>  jobs;
+  std::vector<double>   srow_cost;   // modelled tensor cycles per column tile
+  uint64_t a_bytes = 0;              // bytes of packed A images
+  int64_t  nztot = 0;                // sum over blocks of h*w (the reference's VBR::nztot)
+  int64_t  n_blocks = 0;
+  int64_t  rows = 0;                 // C rows covered by the shard
+  uint32_t max_chunk_bytes = 0;
+};
+
+struct Assignment {          // depends on n (columns of B) and the grid
+  std::vector<Item>    items;
+  std::vector<int32_t> cta_ptr;
+  std::vector<int32_t> cta_items;
+  int grid = 0;
+  double max_cta_cost = 0, mean_cta_cost = 0;
+};
+
+// Returns "" on success, otherwise a static error string.
+const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Structure* out);
+const char* build_assignment(const Structure& st, const ScheduleOptions& opt, int64_t n,
+                             Assignment* out);
+
+// Contiguous block-row ranges balanced on nonzero-block area (sum h*w), the
+// partition SURVEY 8(e) prescribes for multi-GPU sharding.  cuts has parts+1 entries.
+void partition_block_rows(int64_t block_rows, const int64_t* row_part, const int64_t* nzcount,
+                          int parts, int64_t* cuts);
+
+}  // namespace sparta

@@ -1,0 +1,473 @@
+// Block-sparse (VBR / BELLPACK) x dense SpMM for sm_100a.
+//
+// Replaces the reference's per-block cublasGemmEx loop over n_streams
+// (src/cuda/cuda_utilities.cpp:146-182), the batched cublasSgemmBatched loop
+// (:831-868) and the cuSPARSE / CUTLASS Blocked-ELL calls (:1617,
+// src/cuda/cutlass_bellpack_lib.cu:157-200) with ONE persistent kernel.
+//
+// Formulation (the reference's "inverted" product, cuda_utilities.cpp:675-690):
+//   Ct[j, r] += sum_k Bt[j, k] * A_blk[r, k]
+// so the fixed dimension (128 columns of B) sits on the tcgen05 M axis and the
+// variable block height h sits on the N axis (any multiple of 16 up to 256):
+// ragged heights cost no padding beyond 16 rows and no dense grid.
+//
+//   warp 0   : TMA producer.  Per chunk: one 2-D tensor load of the B row-panel
+//              (128 columns x 128 bytes of k, SWIZZLE_128B) and one bulk copy of
+//              the chunk's packed A images (already in MMA smem byte order).
+//   warp 1   : single-thread tcgen05.mma issuer; accumulators live in TMEM.
+//              Member segments with adjacent accumulators are fused into one
+//              MMA (N up to 256) so the B panel is read from smem once per run.
+//   warps 2-5: epilogue.  tcgen05.ld -> predicated stores to C; re-zero TMEM.
+//
+// A super-row (several row segments sharing one TMEM allocation) walks the
+// MERGED list of its members' column blocks, so a B panel is fetched once per
+// super-row instead of once per nonzero block.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "spmm_kernel.h"
+
+namespace sparta {
+
+// ------------------------------------------------------------------ PTX glue
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin on an mbarrier phase.  A pipeline bug must not wedge the GPU box, so the
+// wait traps after 5 s instead of spinning forever.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (((++spins) & 0x3FF) == 0 && global_timer_ns() - t0 > 5000000000ull) {
+      printf("sparta spmm: mbarrier wait timed out (cta %d thread %d tag %d parity %u)\n",
+             blockIdx.x, threadIdx.x, tag, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes,
+                                          uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (tcgen05): start address
+// >> 4 in [0,14), LBO = 1 in [16,30) (ignored for swizzled K-major), SBO = 1024
+// B >> 4 in [32,46) (8 rows x 128 B per swizzle atom), version 1 in [46,48),
+// layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+struct StageMeta {
+  uint32_t mask;
+  int32_t  ksteps;
+  uint32_t a_off;   // byte offset of this chunk's images inside the A ring
+  uint32_t pad_;
+};
+
+// ------------------------------------------------------------------ kernel
+template <bool kTf32>
+__global__ void __launch_bounds__(kSpmmThreads, 1)
+spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles.
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const int P = p.panel_stages;
+  const uint32_t panels = base;
+  const uint32_t a_ring = base + P * kPanelBytes;
+  uint8_t* ctrl = smem + P * kPanelBytes + p.a_ring_bytes;
+  const uint32_t ctrl_u = a_ring + p.a_ring_bytes;
+  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | meta[8] |
+  //              tmem_ptr | starts[8] | cols[33]
+  const uint32_t bar_full = ctrl_u;
+  const uint32_t bar_empty = ctrl_u + 64;
+  const uint32_t bar_acc_full = ctrl_u + 128;
+  const uint32_t bar_acc_empty = ctrl_u + 144;
+  StageMeta* meta = reinterpret_cast<StageMeta*>(ctrl + 160);
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(ctrl + 288);
+  uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 320);
+  int32_t* s_col = reinterpret_cast<int32_t*>(ctrl + 352);  // 33 ints
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);
+      mbar_init(bar_acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_s))),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int it_begin = p.cta_ptr[blockIdx.x];
+  const int it_end = p.cta_ptr[blockIdx.x + 1];
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t RB = static_cast<uint32_t>(p.a_ring_bytes);
+      uint32_t iss = 0, rel = 0, head = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        const Item item = p.items[p.cta_items[it]];
+        const SuperRow sr = p.srows[item.srow];
+        for (int c = 0; c < sr.chunk_count; ++c) {
+          const Chunk ch = p.chunks[sr.chunk_begin + c];
+          // stage slot: the use that last occupied it must have been released
+          while (iss >= static_cast<uint32_t>(P) && rel + P <= iss) {
+            mbar_wait(bar_empty + 8 * (rel % P), (rel / P) & 1, 1);
+            ++rel;
+          }
+          // contiguous space in the A ring (FIFO release order)
+          const uint32_t bytes = ch.a_bytes;
+          uint32_t off;
+          for (;;) {
+            if (rel == iss) { off = 0; break; }
+            const uint32_t tail = starts[rel % P];
+            if (head > tail) {
+              if (head + bytes <= RB) { off = head; break; }
+              if (bytes <= tail) { off = 0; break; }
+            } else if (head + bytes <= tail) {
+              off = head;
+              break;
+            }
+            mbar_wait(bar_empty + 8 * (rel % P), (rel / P) & 1, 2);
+            ++rel;
+          }
+          const uint32_t s = iss % P;
+          starts[s] = off;
+          head = off + bytes;
+          meta[s].mask = ch.mask;
+          meta[s].ksteps = ch.ksteps;
+          meta[s].a_off = off;
+          const uint32_t full = bar_full + 8 * s;
+          mbar_arrive_expect_tx(full, kPanelBytes + bytes);
+          tma_load_2d(panels + s * kPanelBytes, &tmap_b, ch.k0, item.j0, full);
+          const uint8_t* src = p.a_packed + static_cast<size_t>(ch.a_off16) * 16;
+          for (uint32_t done = 0; done < bytes; done += 32768u) {
+            const uint32_t piece = min(32768u, bytes - done);
+            bulk_load(a_ring + off + done, src + done, piece, full);
+          }
+          ++iss;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t use = 0;        // pipeline uses consumed
+    uint32_t acc_use[2] = {0, 0};
+    int local = 0;
+    for (int it = it_begin; it < it_end; ++it, ++local) {
+      const Item item = p.items[p.cta_items[it]];
+      const SuperRow sr = p.srows[item.srow];
+      __syncwarp();
+      if (lane < sr.seg_count) s_col[lane] = p.segs[sr.seg_begin + lane].tmem_col;
+      if (lane == 0) s_col[sr.seg_count] = sr.n_cols;
+      __syncwarp();
+      if (lane == 0) {
+        const int as = (p.acc_stages == 2) ? (local & 1) : 0;
+        mbar_wait(bar_acc_empty + 8 * as, acc_use[as] & 1, 3);
+        ++acc_use[as];
+        tc_fence_after();
+        const uint32_t acc_base = tmem_base + as * p.acc_stage_cols;
+        for (int c = 0; c < sr.chunk_count; ++c, ++use) {
+          const uint32_t s = use % P;
+          mbar_wait(bar_full + 8 * s, (use / P) & 1, 4);
+          tc_fence_after();
+          uint32_t mask = meta[s].mask;
+          const int ksteps = meta[s].ksteps;
+          uint32_t a_addr = a_ring + meta[s].a_off;
+          const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
+          while (mask) {
+            const int m0 = __ffs(mask) - 1;
+            const uint32_t inv = ~(mask >> m0);
+            const int len = inv ? (__ffs(inv) - 1) : (32 - m0);
+            const int mend = m0 + len;
+            int m = m0;
+            while (m < mend) {
+              const int mstart = m;
+              const int col0 = s_col[mstart];
+              ++m;
+              while (m < mend && s_col[m + 1] - col0 <= 256) ++m;
+              const int N = s_col[m] - col0;
+              const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(N >> 3) << 17);
+              const uint64_t adesc = smem_desc(a_addr);
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {
+                // +32 bytes along K inside the 128-byte swizzle row
+                tc_mma<kTf32>(acc_base + col0, pdesc + 2 * k, adesc + 2 * k, idesc);
+              }
+              a_addr += static_cast<uint32_t>(N) * 128u;
+            }
+            const uint32_t run = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
+            mask &= ~(run << m0);
+          }
+          tc_commit(bar_empty + 8 * s);
+        }
+        tc_commit(bar_acc_full + 8 * as);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // Zero every accumulator once; the MMAs always accumulate and the epilogue
+    // re-zeroes what it drains.
+    for (int c0 = 0; c0 < 512; c0 += 16) tmem_st16_zero(t_lane + c0);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(bar_acc_empty);
+      if (p.acc_stages == 2) mbar_arrive(bar_acc_empty + 8);
+    }
+    uint32_t acc_use[2] = {0, 0};
+    int local = 0;
+    const bool c_aligned = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+    for (int it = it_begin; it < it_end; ++it, ++local) {
+      const Item item = p.items[p.cta_items[it]];
+      const SuperRow sr = p.srows[item.srow];
+      const int as = (p.acc_stages == 2) ? (local & 1) : 0;
+      mbar_wait(bar_acc_full + 8 * as, acc_use[as] & 1, 5);
+      ++acc_use[as];
+      tc_fence_after();
+      const uint32_t t_acc = t_lane + as * p.acc_stage_cols;
+      const int j = item.j0 + q * 32 + lane;
+      const bool jv = j < p.n;
+      float* cj = p.C + static_cast<int64_t>(j) * p.c_sj;
+      for (int sidx = 0; sidx < sr.seg_count; ++sidx) {
+        const Segment sg = p.segs[sr.seg_begin + sidx];
+        const bool vec_ok = c_aligned && p.c_sr == 1 && (p.c_sj & 3) == 0 && (sg.c_row0 & 3) == 0;
+        for (int c0 = 0; c0 < sg.h_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + sg.tmem_col + c0, v);
+          tmem_wait_ld();
+          tmem_st16_zero(t_acc + sg.tmem_col + c0);
+          if (jv) {
+            float* dst = cj + static_cast<int64_t>(sg.c_row0 + c0) * p.c_sr;
+            if (vec_ok && c0 + 16 <= sg.h) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                       __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                float4* d4 = reinterpret_cast<float4*>(dst) + g;
+                if (p.accumulate) {
+                  const float4 old = *d4;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *d4 = o;
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                if (c0 + r < sg.h) {
+                  float o = __uint_as_float(v[r]);
+                  float* d = dst + static_cast<int64_t>(r) * p.c_sr;
+                  if (p.accumulate) o += *d;
+                  *d = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(512u)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ launch
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total, int64_t ldk,
+                        int precision, int grid, cudaStream_t stream, const char** err) {
+  *err = "";
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    *err = "cuTensorMapEncodeTiled entry point not available";
+    return cudaErrorNotSupported;
+  }
+  const int esize = prec_esize(precision);
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(p.n)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldk) * esize};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), kTileJ};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = precision == PREC_BF16   ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : precision == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUresult r = encode(&tmap, dt, 2, const_cast<void*>(b_dev), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled failed for the B operand";
+    return cudaErrorInvalidValue;
+  }
+  const int smem = spmm_smem_bytes(p.panel_stages, p.a_ring_bytes);
+  if (smem > kSmemMax || p.panel_stages < 2 || p.panel_stages > kMaxPanelStages) {
+    *err = "invalid pipeline configuration (shared memory)";
+    return cudaErrorInvalidConfiguration;
+  }
+  cudaError_t e;
+  if (p.kind_tf32) {
+    e = cudaFuncSetAttribute(spmm_vbr_sm100<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem);
+    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
+    spmm_vbr_sm100<true><<<grid, kSpmmThreads, smem, stream>>>(tmap, p);
+  } else {
+    e = cudaFuncSetAttribute(spmm_vbr_sm100<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem);
+    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
+    spmm_vbr_sm100<false><<<grid, kSpmmThreads, smem, stream>>>(tmap, p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) *err = "spmm kernel launch";
+  return e;
+}
+
+}  // namespace sparta

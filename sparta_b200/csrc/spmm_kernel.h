@@ -1,0 +1,48 @@
+// Launch interface of the sm_100a block-sparse x dense kernel (spmm_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sched_types.h"
+
+namespace sparta {
+
+struct SpmmParams {
+  const Item*     items;
+  const int32_t*  cta_ptr;      // [grid + 1] ranges into cta_items
+  const int32_t*  cta_items;    // item ids grouped per CTA (host LPT assignment)
+  const SuperRow* srows;
+  const Segment*  segs;
+  const Chunk*    chunks;
+  const uint8_t*  a_packed;     // packed A images (see PackJob)
+  float*          C;
+  int64_t         c_sr;         // element stride of C between rows
+  int64_t         c_sj;         // element stride of C between columns
+  int32_t         n;            // columns of B and C
+  int32_t         accumulate;   // 1: C += A*B (reference beta = 1), 0: C = A*B
+  uint32_t        idesc_base;   // tcgen05 instruction descriptor, N field empty
+  int32_t         kind_tf32;    // 0: kind::f16 (bf16/fp16), 1: kind::tf32
+  int32_t         panel_stages; // pipeline depth (<= 8)
+  int32_t         a_ring_bytes; // bytes of the A-image ring (multiple of 1024)
+  int32_t         acc_stages;   // 1 or 2 TMEM accumulator stages
+  int32_t         acc_stage_cols; // 512 / acc_stages
+};
+
+constexpr int kSpmmThreads   = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kMaxPanelStages = 8;
+constexpr int kSmemCtrlBytes = 1024;  // barriers + metadata block at the end
+constexpr int kSmemMax       = 232448; // 227 KB opt-in limit per CTA
+
+// Bytes of dynamic shared memory for a configuration (includes 1 KB slack used
+// to align the base to 1024 for SWIZZLE_128B).
+static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes) {
+  return 1024 + panel_stages * kPanelBytes + a_ring_bytes + kSmemCtrlBytes;
+}
+
+// B operand as the kernel reads it: [n][ldk] elements (k contiguous), converted
+// to the compute precision.  Returns cudaSuccess or the failing status; *err
+// gets a static description on failure.
+cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
+                        int64_t ldk, int precision, int grid, cudaStream_t stream,
+                        const char** err);
+
+}  // namespace sparta

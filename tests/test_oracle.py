@@ -1,0 +1,134 @@
+"""The oracle (oracle/sparta_oracle.cpp) pinned against the reference: golden vectors captured
+from the compiled reference, and -- where oracle/_ref exists -- the unmodified reference itself
+on randomised inputs.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from sparta_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+with open(os.path.join(GOLDEN, "reference_vectors.json")) as f:
+    VECTORS = json.load(f)
+
+ARRAY_KEYS = ["csr_rowptr", "csr_colind", "csr_val", "grouping", "row_part", "nzcount", "jab", "mab"]
+SCALAR_KEYS = ["csr_rows", "csr_cols", "csr_nnz", "comparison_counter", "merge_counter",
+               "VBR_nzcount", "VBR_nzblocks_count", "VBR_longest_row", "rows", "cols", "block_rows",
+               "block_cols", "block_col_size", "nztot"]
+FLOAT_KEYS = ["average_merge_tau", "average_row_distance", "VBR_average_height"]
+
+
+def _same(res, rec):
+    for k in ARRAY_KEYS:
+        assert np.array_equal(res[k], np.asarray(rec[k], dtype=res[k].dtype)), k
+    for k in SCALAR_KEYS:
+        assert res[k] == rec[k], k
+    for k in FLOAT_KEYS:
+        if rec[k] is None:
+            assert res[k] != res[k], k
+        else:
+            assert np.float32(res[k]) == np.float32(rec[k]), k
+
+
+@pytest.mark.parametrize("idx", range(len(VECTORS)))
+def test_oracle_matches_golden_structure_and_product(oracle, idx):
+    rec = VECTORS[idx]
+    res = oracle.run(os.path.join(GOLDEN, rec["file"]), **rec["flags"])
+    _same(res, rec)
+    n = rec["n"]
+    Cm = oracle.vbr_multiply(res, np.asarray(rec["B"], dtype=np.float32), n)
+    assert np.array_equal(Cm.reshape(-1), np.asarray(rec["C"], dtype=np.float32))
+
+
+def test_survey_vectors_test_matrix(oracle):
+    """The numbers printed in SURVEY.md 8(c) for data/TEST_matrix_weighted.el -b 3 -t 0.6."""
+    res = oracle.run(os.path.join(GOLDEN, "TEST_matrix_weighted.el"), b=3, t=0.6)
+    assert res["grouping"].tolist() == [0, 1, 1, 1, 0, 5, 0, 0, 8]
+    assert res["row_part"].tolist() == [0, 4, 7, 8, 9]
+    assert res["nzcount"].tolist() == [0, 3, 1, 1]
+    assert res["jab"].tolist() == [0, 1, 2, 2, 0]
+    assert res["mab"].astype(int).tolist() == [0, 0, 0, 0, 0, 1, 5, 0, 0, 0, 0, 1, 0, 0, 0, 8, 1, 0, 0,
+                                               1, 0, 0, 0, 3, 7, 1, 8, 2, 0, 0, 0, 5, 0]
+    assert (res["VBR_nzcount"], res["VBR_nzblocks_count"], res["VBR_longest_row"]) == (33, 5, 3)
+    assert (res["merge_counter"], res["comparison_counter"]) == (5, 13)
+    B = (np.arange(18) + 1).astype(np.float32)
+    Cm = oracle.vbr_multiply(res, B, 2)
+    assert Cm.tolist() == [[0, 0, 0, 0, 126, 22, 102, 14, 10], [0, 0, 0, 0, 306, 49, 219, 32, 55]]
+
+
+def test_similarities_vectors(oracle):
+    """test/general/TEST_similarities.cpp:14-36 values probed in SURVEY 8(c)."""
+    a, b = [1, 2, 5, 10, 12, 20], [0, 2, 4, 10, 16]
+    assert oracle.distance(0, a, 1, b, 1, 3) == 3.0
+    assert oracle.distance(1, a, 1, b, 1, 3) == 0.5
+    assert oracle.distance(0, a, 1, b, 1, 1) == 7.0
+    assert abs(oracle.distance(1, a, 1, b, 1, 1) - 0.777778) < 1e-6
+    assert oracle.distance(2, a, 1, b, 1, 3) == 3.0 and oracle.distance(3, a, 1, b, 1, 3) == 0.5
+
+
+def test_csr_vs_vbr_multiply_equal(oracle):
+    """test/general/TEST_matrices.cpp:9-57: fixed blocking, B = ones with 5 columns; the CSR and
+    VBR products must be identical (un-permuted rows because the blocking is fixed-size)."""
+    res = oracle.run(os.path.join(GOLDEN, "TEST_matrix_weighted.el"), a=2, b=3, B=3)
+    B = np.ones(5 * 9, dtype=np.float32)
+    Cv = oracle.vbr_multiply(res, B, 5)
+    Cc = oracle.csr_multiply(res["csr_rows"], res["csr_rowptr"], res["csr_colind"], res["csr_val"], 0, B, 5)
+    assert np.array_equal(Cv, Cc)
+    assert Cv[0].tolist() == [0, 20, 3, 13, 0, 2, 0, 0, 5]
+
+
+def test_merge_rows_is_not_a_union(oracle):
+    """utilities.cpp:145-173 drops the tail of A above the last B entry inside A's range."""
+    assert oracle.merge_rows([1, 5, 9], [3]).tolist() == [1, 3]
+    assert oracle.merge_rows([1, 5], [7]).tolist() == [7]
+    assert oracle.merge_rows([1, 5, 9], []).tolist() == []
+    assert oracle.merge_rows([1, 5, 9], [5, 20]).tolist() == [1, 5, 20]
+
+
+def test_bellpack_repack(oracle):
+    res = oracle.run(os.path.join(GOLDEN, "rmat8.el"), P=1, a=2, b=16, B=16, F=1)
+    bs, ind, vals = oracle.bellpack_from_vbr(res)
+    assert bs == 16 and ind.shape[0] == res["rows"] // 16 and ind.shape[1] == res["nzcount"].max()
+    from sparta_b200.api import VBR, bellpack_from_vbr
+    v = VBR(res["rows"], res["cols"], 16, res["row_part"], res["nzcount"], res["jab"], res["mab"])
+    bs2, ind2, vals2 = bellpack_from_vbr(v)
+    assert bs2 == bs and np.array_equal(ind, ind2) and np.array_equal(vals, vals2)
+
+
+FLAG_SETS = [
+    dict(a=3, b=8, t=0.6), dict(a=4, b=8, t=0.6), dict(a=5, b=8, B=8, t=0.6),
+    dict(a=5, b=16, B=32, t=0.3), dict(a=5, b=8, B=7, t=0.9), dict(a=2, b=8, B=8, F=1),
+    dict(a=3, b=8, B=8, t=0.5, F=1), dict(a=3, b=4, t=0.4, m=0), dict(a=5, b=8, B=8, t=0.6, r=2, s=7),
+    dict(a=3, b=8, t=0.6, r=-1), dict(a=4, b=8, t=1.0), dict(a=4, b=8, t=0.0), dict(a=6, b=8),
+    dict(a=5, b=8, B=8, t=0.6, g=1), dict(a=3, b=8, t=0.6, g=1, p=0), dict(a=5, b=64, B=64, t=0.6),
+]
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS, ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()))
+@pytest.mark.parametrize("kind", ["rmat", "er_weighted"])
+def test_oracle_equals_reference_build(oracle, reference, tmp_path, kind, flags):
+    """Bit-for-bit against the unmodified reference sources (skipped where oracle/_ref is absent)."""
+    if kind == "rmat":
+        r, c = synth.rmat_edges(9, 6000, seed=1)
+        r, c = synth.pin_shape(r, c, 512, 512)
+        path = str(tmp_path / "m.el")
+        synth.write_el(path, r, c)
+        flags = dict(flags, P=1)
+    else:
+        rng = np.random.default_rng(5)
+        r, c = synth.er_edges(300, 280, 0.02, seed=2)
+        path = str(tmp_path / "m.el")
+        synth.write_el(path, r, c, vals=rng.uniform(-1, 1, len(r)))
+    ro = oracle.run(path, **flags)
+    rr = reference.run(path, **flags)
+    for k, a in ro.items():
+        b = rr[k]
+        if isinstance(a, np.ndarray):
+            assert np.array_equal(a, b), k
+        else:
+            assert a == b or (a != a and b != b), k
+    rng = np.random.default_rng(0)
+    B = rng.uniform(0, 1, size=(3, int(rr["cols"]))).astype(np.float32)
+    assert np.array_equal(oracle.vbr_multiply(rr, B, 3), reference.vbr_multiply(rr, B, 3))

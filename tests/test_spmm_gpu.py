@@ -1,0 +1,260 @@
+"""Parity tests proper: the sm_100a kernel, called through the C ABI, against the oracle
+(oracle/sparta_oracle.cpp restating VBR::multiply, src/general/vbr.cpp:323-372).
+
+Tolerances (norm = max|C - Cref| / max|Cref|):
+  * integer-valued operands (exact in bf16/fp16/tf32, sums exact in fp32): bit-exact;
+  * general operands vs the oracle fed THE SAME fp32 inputs: <= 2e-2 for bf16/fp16;
+  * general operands vs the oracle fed the operands rounded to the kernel's input precision
+    (only the fp32 accumulation order differs): <= 1e-5 for tf32, bf16 and fp16.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sparta_b200
+from sparta_b200 import synth
+from sparta_b200.api import VBR, bellpack_from_vbr, bellpack_spmm, vbr_spmm
+from tests.util import random_vbr, rel_err, round_to, vbr_to_dense
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL_ROUNDED = 1e-5
+TOL_UNROUNDED = {"bf16": 2e-2, "fp16": 2e-2, "tf32": 2e-3}
+
+
+def gpu_multiply(v, Bm, n, precision="bf16", **opts):
+    """C as [n, rows] through the handle API."""
+    h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], v["block_col_size"], v["row_part"],
+                                    v["nzcount"], v["jab"], v["mab"], precision=precision, **opts)
+    try:
+        h.set_B(Bm, Bm.shape[1], n)
+        h.run()
+        out = np.zeros((n, v["rows"]), dtype=np.float32)
+        h.get_C(out, v["rows"])
+        assert h.stats()["kernel_launches"] == 1
+        return out
+    finally:
+        h.close()
+
+
+def rounded(v, precision):
+    w = dict(v)
+    w["mab"] = round_to(v["mab"], precision)
+    return w
+
+
+CASES = [
+    (6, 96, 16, [16] * 6, 0.5, 40, {}),
+    (5, 70, 16, [3, 17, 1, 64, 30], 0.6, 130, {}),
+    (4, 64, 3, [4, 3, 1, 1], 0.7, 2, {}),
+    (3, 300, 100, [64, 64, 20], 0.8, 16, {}),
+    (7, 128, 64, [64] * 7, 0.4, 256, {"acc_cols": 512}),
+    (2, 64, 32, [200, 70], 1.0, 8, {}),
+    (40, 64, 8, [1] * 40, 0.3, 8, {"acc_cols": 512}),
+    (3, 64, 16, [5, 7, 9], 0.0, 8, {}),                    # no nonzero block at all -> C = 0
+    (24, 1024, 64, [64] * 24, 0.5, 384, {}),               # several items per CTA, pipeline wraps
+    (9, 640, 64, [64, 63, 30, 64, 1, 128, 7, 64, 33], 0.7, 200, {"acc_cols": 512, "panel_stages": 3}),
+    (16, 512, 64, [64] * 16, 1.0, 128, {"panel_stages": 2}),
+    (3, 2048, 128, [256, 100, 16], 0.9, 64, {"seg_rows": 256, "acc_cols": 512}),
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_integer_operands_bit_exact(oracle, lib, case, precision):
+    block_rows, cols, w, heights, density, n, opts = CASES[case]
+    rng = np.random.default_rng(100 + case)
+    v = random_vbr(rng, block_rows, cols, w, heights, density, values="int")
+    Bm = rng.integers(-3, 4, size=(n, cols)).astype(np.float32)
+    Cg = gpu_multiply(v, Bm, n, precision, **opts)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    assert np.array_equal(Cg, Cref)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
+@pytest.mark.parametrize("case", [1, 3, 8, 9, 11])
+def test_real_operands_within_tolerance(oracle, lib, case, precision):
+    block_rows, cols, w, heights, density, n, opts = CASES[case]
+    rng = np.random.default_rng(200 + case)
+    v = random_vbr(rng, block_rows, cols, w, heights, density, values="uniform")
+    Bm = rng.random((n, cols), dtype=np.float32)  # uniform(0,1) like cuda_multiply.cpp:36-44
+    Cg = gpu_multiply(v, Bm, n, precision, **opts)
+    C_same_inputs = oracle.vbr_multiply(v, Bm, n)
+    C_rounded = oracle.vbr_multiply(rounded(v, precision), round_to(Bm, precision), n)
+    assert rel_err(Cg, C_rounded) <= TOL_ROUNDED
+    assert rel_err(Cg, C_same_inputs) <= TOL_UNROUNDED[precision]
+
+
+with open(os.path.join(GOLDEN, "reference_vectors.json")) as f:
+    VECTORS = json.load(f)
+
+
+@pytest.mark.parametrize("idx", range(len(VECTORS)))
+def test_golden_reference_products(lib, idx):
+    """C of the compiled reference's own VBR::multiply on its own VBR arrays (tests/golden)."""
+    rec = VECTORS[idx]
+    v = {k: (np.asarray(rec[k]) if isinstance(rec[k], list) else rec[k])
+         for k in ("rows", "cols", "block_col_size", "row_part", "nzcount", "jab", "mab")}
+    n = rec["n"]
+    Bm = np.asarray(rec["B"], dtype=np.float32).reshape(n, rec["cols"])
+    Cref = np.asarray(rec["C"], dtype=np.float32).reshape(n, rec["rows"])
+    Cg = gpu_multiply(v, Bm, n, "tf32")
+    if rec["file"] == "er_weighted.el":   # weights have 3 decimals: not exact in tf32
+        assert rel_err(Cg, Cref) <= TOL_UNROUNDED["tf32"]
+    else:
+        assert np.array_equal(Cg, Cref)
+    Cg = gpu_multiply(v, Bm, n, "bf16")
+    if rec["file"] == "er_weighted.el":
+        assert rel_err(Cg, Cref) <= TOL_UNROUNDED["bf16"]
+    else:
+        assert np.array_equal(Cg, Cref)
+
+
+def test_one_shot_reference_signature(oracle, lib):
+    """sparta_vbr_spmm = upload + multiply + download, the data flow of
+    cublas_fixed_blocks_multiply (cuda_utilities.cpp:39-209)."""
+    rng = np.random.default_rng(5)
+    v = random_vbr(rng, 10, 320, 32, [32] * 10, 0.5, values="int")
+    Bm = rng.integers(-3, 4, size=(96, 320)).astype(np.float32)
+    A = VBR(v["rows"], v["cols"], 32, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+    Cg, dt = vbr_spmm(A, Bm, 96, "bf16")
+    assert dt > 0
+    assert np.array_equal(Cg, oracle.vbr_multiply(v, Bm, 96))
+
+
+def test_accumulate_beta_one_and_idempotence(oracle, lib):
+    rng = np.random.default_rng(6)
+    v = random_vbr(rng, 6, 256, 64, [64, 20, 64, 1, 64, 64], 0.6, values="int")
+    n = 72
+    Bm = rng.integers(-3, 4, size=(n, 256)).astype(np.float32)
+    C0 = rng.integers(-5, 6, size=(n, v["rows"])).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n, C_init=C0)   # reference semantics: C += A*B
+    h = sparta_b200.Handle.from_vbr(v["rows"], 256, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    accumulate=1)
+    h.set_B(Bm, 256, n)
+    h.set_C(C0, v["rows"])
+    h.run()
+    out = np.zeros_like(C0)
+    h.get_C(out, v["rows"])
+    assert np.array_equal(out, Cref)
+    h.close()
+    # accumulate = 0: running twice gives the same C (no hidden state between launches)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 256, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+    h.set_B(Bm, 256, n)
+    h.run()
+    a = h.get_C(np.zeros_like(C0), v["rows"]).copy()
+    h.run()
+    h.run()
+    b = h.get_C(np.zeros_like(C0), v["rows"])
+    assert np.array_equal(a, b) and np.array_equal(a, oracle.vbr_multiply(v, Bm, n))
+    # new B with a different n on the same handle
+    B2 = rng.integers(-3, 4, size=(200, 256)).astype(np.float32)
+    h.set_B(B2, 256, 200)
+    h.run()
+    c = h.get_C(np.zeros((200, v["rows"]), np.float32), v["rows"])
+    assert np.array_equal(c, oracle.vbr_multiply(v, B2, 200))
+    h.close()
+
+
+def test_padded_leading_dimensions(oracle, lib):
+    rng = np.random.default_rng(7)
+    v = random_vbr(rng, 5, 100, 16, [16, 5, 16, 16, 11], 0.7, values="int")
+    n, ldb, ldc = 33, 120, 80
+    Bfull = rng.integers(-3, 4, size=(n, ldb)).astype(np.float32)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 100, 16, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+    h.set_B(Bfull, ldb, n)
+    h.run()
+    out = np.full((n, ldc), -7.0, dtype=np.float32)
+    h.get_C(out, ldc)
+    h.close()
+    Cref = oracle.vbr_multiply(v, Bfull, n, ldb=ldb)
+    assert np.array_equal(out[:, :v["rows"]], Cref)
+    assert np.all(out[:, v["rows"]:] == -7.0)
+
+
+def test_row_block_shards_reassemble(oracle, lib):
+    """Multi-GPU partition on one device: every shard computes its own C slab."""
+    rng = np.random.default_rng(8)
+    heights = rng.integers(1, 100, size=30)
+    v = random_vbr(rng, 30, 512, 64, heights, 0.4, values="int")
+    n = 130
+    Bm = rng.integers(-3, 4, size=(n, 512)).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], 4)
+    slabs = []
+    for i in range(4):
+        lo, hi = int(cuts[i]), int(cuts[i + 1])
+        rows_i = int(v["row_part"][hi] - v["row_part"][lo])
+        h = sparta_b200.Handle.from_vbr(v["rows"], 512, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                        block_row_begin=lo, block_row_end=hi)
+        h.set_B(Bm, 512, n)
+        h.run()
+        slabs.append(h.get_C(np.zeros((n, rows_i), np.float32), rows_i) if rows_i else np.zeros((n, 0), np.float32))
+        assert h.stats()["rows"] == rows_i
+        h.close()
+    assert np.array_equal(np.concatenate(slabs, axis=1), Cref)
+
+
+def test_bellpack_path_row_major(oracle, lib):
+    """-M 3 / -M 8 replacement: Blocked-ELL A, row-major B and C (cuda_utilities.cpp:1581-1591)."""
+    res = oracle.run(os.path.join(GOLDEN, "rmat8.el"), P=1, a=2, b=16, B=16, F=1)
+    A = VBR(res["rows"], res["cols"], 16, res["row_part"], res["nzcount"], res["jab"], res["mab"])
+    bs, ind, vals = bellpack_from_vbr(A)
+    bs_o, ind_o, vals_o = oracle.bellpack_from_vbr(res)
+    assert bs == bs_o and np.array_equal(ind, ind_o) and np.array_equal(vals, vals_o)
+    rng = np.random.default_rng(9)
+    n = 50
+    B_rm = rng.integers(-3, 4, size=(res["cols"], n)).astype(np.float32)   # row-major cols x n
+    Cg, dt = bellpack_spmm(res["rows"], res["cols"], bs, ind, vals, B_rm, n, "bf16")
+    Cref = oracle.vbr_multiply(res, np.ascontiguousarray(B_rm.T), n)       # [n, rows]
+    assert np.array_equal(Cg, Cref.T)
+
+
+def test_device_resident_B_and_C(oracle, lib):
+    """B arrives as a device pointer (the NCCL-broadcast path) and C is read back on the device."""
+    import torch
+    rng = np.random.default_rng(10)
+    v = random_vbr(rng, 8, 256, 64, [64] * 8, 0.5, values="int")
+    n = 256
+    Bm = rng.integers(-3, 4, size=(n, 256)).astype(np.float32)
+    Bd = torch.from_numpy(Bm).cuda()
+    h = sparta_b200.Handle.from_vbr(v["rows"], 256, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+    h.set_B_device(Bd.data_ptr(), 256, n)
+    h.run()
+    Cd = torch.zeros((n, v["rows"]), dtype=torch.float32, device="cuda")
+    h.get_C_device(Cd.data_ptr(), v["rows"])
+    torch.cuda.synchronize()
+    assert np.array_equal(Cd.cpu().numpy(), oracle.vbr_multiply(v, Bm, n))
+    h.close()
+
+
+def test_config2_shape_er_bellpack_blocking(lib):
+    """BASELINE config #2 at full size: ER 16384^2, fixed 64x64 blocks, ~10% block density,
+    n = 1024, bf16.  Too big for the serial oracle, so: (i) sampled block-rows recomputed in
+    fp64 from the bf16-rounded operands, (ii) linearity C(B1 + B2) = C(B1) + C(B2) on
+    integer operands (exact)."""
+    N, w, n = 16384, 64, 1024
+    r, c = synth.er_edges(N, N, 2.57e-5, seed=1)
+    r, c = synth.pin_shape(r, c, N, N)
+    rowptr, colind, val = synth.csr_from_edges(r, c, N)
+    from sparta_b200.lib import host_vbr_fill
+    v = host_vbr_fill(N, N, rowptr, colind, None, np.arange(N) // w, w, w, True)
+    assert v["block_rows"] == 256 and 5500 < len(v["jab"]) < 7500
+    rng = np.random.default_rng(2)
+    B1 = rng.integers(-3, 4, size=(n, N)).astype(np.float32)
+    B2 = rng.integers(-3, 4, size=(n, N)).astype(np.float32)
+    h = sparta_b200.Handle.from_vbr(N, N, w, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+    outs = []
+    for Bm in (B1, B2, B1 + B2):
+        h.set_B(Bm, N, n)
+        h.run()
+        outs.append(h.get_C(np.zeros((n, N), np.float32), N).copy())
+    h.close()
+    assert np.array_equal(outs[0] + outs[1], outs[2])
+    A = vbr_to_dense({**v, "row_part": v["row_part"][:3], "nzcount": v["nzcount"][:2],
+                      "rows": 128})  # first two block-rows
+    ref = (A @ B1.T.astype(np.float64)).T
+    assert np.array_equal(outs[0][:, :128], ref.astype(np.float32))
