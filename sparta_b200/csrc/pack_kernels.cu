@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) pack_a_images_kernel(const float* __restr
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = c * epc + e;
-      v[e] = (e < epc && r < job.h && k < job.k_count)
+      const int k = job.k_lo + c * epc + e;   // block-local k
+      v[e] = (e < epc && r < job.h && k >= 0 && k < job.k_w)
                  ? src[job.src_base + static_cast<int64_t>(r) * job.src_rs +
                        static_cast<int64_t>(k) * job.src_ks]
                  : 0.f;

@@ -52,8 +52,11 @@ struct PackJob {
   int64_t src_ks;     // element stride between consecutive k of the block
   int32_t h;          // valid rows
   int32_t h_pad;
-  int32_t k_count;    // valid k in this slab (<= 128/esize)
+  int32_t k_lo;       // block-local k of image column 0 (negative when the slab starts
+                      // before the block: TMA needs a 16-byte aligned k coordinate)
+  int32_t k_w;        // block width w: image column kk holds k = k_lo + kk iff 0 <= k < w
   uint32_t dst_off16; // destination offset, 16-byte units
+  int32_t pad_[3];
 };
 
 enum Precision : int32_t { PREC_BF16 = 0, PREC_FP16 = 1, PREC_TF32 = 2 };

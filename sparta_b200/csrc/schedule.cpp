@@ -24,7 +24,7 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
   const int esize = prec_esize(opt.precision);
   const int katom = 128 / esize;    // k elements per 128-byte swizzle row
   const int kstep = 32 / esize;     // k elements per MMA (K = 16 for 16-bit, 8 for tf32)
-  const int64_t atoms = (br.w + katom - 1) / katom;
+  const int kalign = 16 / esize;    // TMA needs a 16-byte aligned start along k
 
   // 1. segments, tagged with their block-row and row offset inside it
   struct SegSrc { int64_t b; int64_t row_off; };
@@ -86,15 +86,20 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
         mask |= 1u << merged[i1].second;
         ++i1;
       }
+      // K slabs of this column block: start at the 16-byte aligned k at or below jb*w
+      const int64_t kblk = jb * br.w;
+      const int64_t ka = kblk / kalign * kalign;
+      const int shift = static_cast<int>(kblk - ka);
+      const int64_t atoms = (shift + br.w + katom - 1) / katom;
       for (int64_t a = 0; a < atoms; ++a) {
-        const int64_t kbeg = a * katom;
-        const int k_count = static_cast<int>(std::min<int64_t>(katom, br.w - kbeg));
+        const int64_t k_lo = a * katom - shift;  // block-local k of image column 0
+        const int k_used = static_cast<int>(std::min<int64_t>(katom, br.w - k_lo));
         Chunk ch{};
-        const int64_t k0 = jb * br.w + kbeg;
+        const int64_t k0 = ka + a * katom;
         if (k0 > INT32_MAX) return "k index exceeds 2^31";
         ch.k0 = static_cast<int32_t>(k0);
         ch.mask = mask;
-        ch.ksteps = (k_count + kstep - 1) / kstep;
+        ch.ksteps = (k_used + kstep - 1) / kstep;
         if ((st.a_bytes >> 4) > UINT32_MAX) return "packed A exceeds 64 GiB";
         ch.a_off16 = static_cast<uint32_t>(st.a_bytes >> 4);
         uint32_t bytes = 0;
@@ -109,10 +114,12 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
           PackJob job;
           job.src_rs = br.rs[b];
           job.src_ks = br.ks[b];
-          job.src_base = br.src[q] + kbeg * job.src_ks + seg_src[s].row_off * job.src_rs;
+          job.src_base = br.src[q] + seg_src[s].row_off * job.src_rs;
           job.h = st.segs[s].h;
           job.h_pad = st.segs[s].h_pad;
-          job.k_count = k_count;
+          job.k_lo = static_cast<int32_t>(k_lo);
+          job.k_w = static_cast<int32_t>(br.w);
+          job.pad_[0] = job.pad_[1] = job.pad_[2] = 0;
           job.dst_off16 = static_cast<uint32_t>((st.a_bytes + bytes) >> 4);
           st.jobs.push_back(job);
           bytes += static_cast<uint32_t>(job.h_pad) * 128u;

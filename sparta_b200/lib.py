@@ -251,7 +251,8 @@ CHUNK_DT = np.dtype([("k0", "<i4"), ("mask", "<u4"), ("a_off16", "<u4"), ("a_byt
                      ("ksteps", "<i4"), ("pad", "<i4", (3,))])
 ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4")])
 JOB_DT = np.dtype([("src_base", "<i8"), ("src_rs", "<i8"), ("src_ks", "<i8"), ("h", "<i4"),
-                   ("h_pad", "<i4"), ("k_count", "<i4"), ("dst_off16", "<u4")])
+                   ("h_pad", "<i4"), ("k_lo", "<i4"), ("k_w", "<i4"), ("dst_off16", "<u4"),
+                   ("pad", "<i4", (3,))])
 _PLAN_DTYPES = [SEG_DT, SROW_DT, CHUNK_DT, ITEM_DT, np.dtype("<i4"), np.dtype("<i4"), JOB_DT]
 _PLAN_NAMES = ["segs", "srows", "chunks", "items", "cta_ptr", "cta_items", "jobs"]
 

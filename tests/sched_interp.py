@@ -21,8 +21,8 @@ def pack_images(jobs, src, a_bytes, esize):
             for c in range(8):
                 vals = np.zeros(epc, dtype=np.float32)
                 for e in range(epc):
-                    k = c * epc + e
-                    if r < job["h"] and k < job["k_count"] and k < katom:
+                    k = int(job["k_lo"]) + c * epc + e
+                    if r < job["h"] and 0 <= k < int(job["k_w"]):
                         vals[e] = src[int(job["src_base"]) + r * int(job["src_rs"]) + k * int(job["src_ks"])]
                 store[base16 + r * 8 + (c ^ (r & 7))] = vals
     return store
@@ -56,6 +56,7 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
             for ch in chunks[sr["chunk_begin"]:sr["chunk_begin"] + sr["chunk_count"]]:
                 panel = np.zeros((128, katom), dtype=np.float32)  # TMA box, zero fill out of bounds
                 k0 = int(ch["k0"])
+                assert (k0 * esize) % 16 == 0, "TMA needs a 16-byte aligned k coordinate"
                 kk = max(0, min(katom, cols - k0))
                 jj = max(0, min(128, n - j0))
                 panel[:jj, :kk] = Bm[j0:j0 + jj, k0:k0 + kk]
