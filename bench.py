@@ -1,0 +1,579 @@
+#!/usr/bin/env python
+"""Headline benchmark: VBR SpMM effective TFLOP/s on nonzero-block FLOPs (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU VBR::multiply
+
+A "step" is one pass of the hot path (C = A*B, one kernel launch) over the workload.  The
+default workload is BASELINE config #3: a seeded R-MAT 65536 x 65536 matrix (density 1e-3,
+pattern-only), blocked with the reference's `-a 5 -b 64 -B 64 -t 0.6` row clustering into VBR,
+times a dense 65536 x 2048 B, bf16 operands, fp32 accumulation.
+
+  value      whole-job TFLOP/s = 2 * nztot * n * K / t, operands resident in HBM, t = CUDA-event
+             time of K back-to-back launches on the launching stream (max over ranks).
+  e2e        the same metric through the one-shot reference-facing C-ABI call
+             (sparta_vbr_spmm: host VBR arrays + host B in, host C out; every H2D/D2H copy,
+             the device-side repack and the kernel are inside the timed region).
+  roofline   tensor bound: achieved = nonzero-block FLOPs per launch / mean launch time,
+             peak = MEASURED_PEAKS.json bf16 (burst when the timed region is < 1 s).
+  cpu_baseline  the reference's own serial VBR::multiply (oracle/_ref, built from the unmodified
+             sources) on a bounded sample of the same workload, 1 thread.
+
+Multi-GPU (torchrun, one rank per GPU): A is sharded by contiguous block-row ranges balanced on
+nonzero-block area, B is replicated with one NCCL broadcast (outside the timed region), C stays
+row-partitioned; no collective runs inside the timed region.  Total work is fixed => "strong".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: scale, density, w, B rows per group, tau, n, blocking algo
+    "rmat16_a5": dict(kind="rmat", scale=16, density=1e-3, w=64, rb=64, tau=0.6, n=2048, algo=5,
+                      desc="R-MAT 65536x65536 (a,b,c,d=.57,.19,.19,.05; 4.29M draws, dedup; seed 1), "
+                           "-P 1 -a 5 -b 64 -B 64 -t 0.6 (Jaccard), B 65536x2048 uniform(0,1) seed 2"),
+    "er14_fixed": dict(kind="er", scale=14, density=2.57e-5, w=64, rb=64, tau=0.0, n=1024, algo=2,
+                       desc="ER 16384x16384 p=2.57e-5 seed 1, -a 2 -F 1 -b 64 -B 64 (10% block density), "
+                            "B 16384x1024"),
+    "rmat12_a5": dict(kind="rmat", scale=12, density=4e-3, w=64, rb=64, tau=0.6, n=512, algo=5,
+                      desc="small R-MAT 4096x4096 for quick checks"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- workload
+
+def make_matrix(wl):
+    from sparta_b200 import synth
+    N = 1 << wl["scale"]
+    if wl["kind"] == "rmat":
+        r, c = synth.rmat_edges(wl["scale"], int(wl["density"] * N * N), seed=1)
+    else:
+        r, c = synth.er_edges(N, N, wl["density"], seed=1)
+    r, c = synth.pin_shape(r, c, N, N)
+    rowptr, colind, _ = synth.csr_from_edges(r, c, N)
+    return N, rowptr, colind
+
+
+def make_grouping(wl, N, rowptr, colind):
+    """Row clustering through the product's host layer (bit-exact with the reference's
+    BlockingEngine::GetGrouping, src/general/blocking.cpp:633)."""
+    from sparta_b200 import lib
+    if wl["algo"] == 2:
+        return np.arange(N, dtype=np.int64) // wl["rb"]
+    cache = os.environ.get("SPARTA_BENCH_CACHE")   # like the reference's .g grouping files (Matrix_Blocking.cpp:24-32)
+    key = None
+    if cache:
+        os.makedirs(cache, exist_ok=True)
+        key = os.path.join(cache, f"grouping_{wl['kind']}{wl['scale']}_{wl['density']}_a{wl['algo']}_b{wl['w']}_B{wl['rb']}_t{wl['tau']}.npy")
+        if os.path.exists(key):
+            return np.load(key)
+    g = lib.host_blocking(N, N, rowptr, colind, algo=wl["algo"], tau=wl["tau"],
+                             block_col_size=wl["w"], row_block_size=wl["rb"], sim_measure=1,
+                             use_pattern=True, use_group=False)
+    if key:
+        np.save(key, g)
+    return g
+
+
+def build_vbr(wl, N, rowptr, colind, grouping):
+    from sparta_b200 import lib
+    return lib.host_vbr_fill(N, N, rowptr, colind, None, grouping, wl["w"], wl["rb"],
+                             force_fixed_size=(wl["algo"] == 2), pattern_only=True)
+
+
+# --------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.1] or [l for _, l in self.lines]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU reference legs
+
+def cpu_reference_sample(v, Bm, n, target_gflop, threads):
+    """Times the reference's serial VBR::multiply (oracle/_ref; else the oracle port) on the first
+    block-rows of the workload holding ~target_gflop of nonzero-block FLOPs.  threads > 1 runs
+    that many independent copies of the serial routine on disjoint block-row ranges."""
+    from oracle.oracle_py import Oracle, Reference
+    kind = "reference" if Reference.available() else "port"
+    impl = Reference() if kind == "reference" else Oracle()
+    rp, nz = v["row_part"], v["nzcount"]
+    w = v["block_col_size"]
+    area = nz * np.diff(rp) * w                      # elements of mab per block-row
+    flops = 2.0 * area * n
+    cum = np.cumsum(flops)
+    nbr = int(np.searchsorted(cum, target_gflop * 1e9) + 1)
+    nbr = max(min(nbr, len(nz)), min(threads, len(nz)))
+    # split [0, nbr) into `threads` contiguous ranges balanced on FLOPs
+    cuts = [0]
+    for t in range(1, threads):
+        cuts.append(int(np.searchsorted(cum[:nbr], cum[nbr - 1] * t / threads)))
+    cuts.append(nbr)
+    jab_off = np.concatenate([[0], np.cumsum(nz)])
+    mab_off = np.concatenate([[0], np.cumsum(area)])
+    subs = []
+    for t in range(threads):
+        lo, hi = cuts[t], cuts[t + 1]
+        if hi <= lo:
+            continue
+        subs.append({
+            "rows": int(rp[hi] - rp[lo]), "cols": v["cols"], "block_col_size": w,
+            "row_part": (rp[lo:hi + 1] - rp[lo]).copy(), "nzcount": nz[lo:hi].copy(),
+            "jab": v["jab"][jab_off[lo]:jab_off[hi]].copy(),
+            "mab": v["mab"][mab_off[lo]:mab_off[hi]],
+        })
+    done = [None] * len(subs)
+
+    def work(i):
+        done[i] = impl.vbr_multiply(subs[i], Bm, n)
+
+    t0 = time.perf_counter()
+    if len(subs) == 1:
+        work(0)
+    else:
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(len(subs))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    dt = time.perf_counter() - t0
+    total = float(cum[nbr - 1])
+    return {"seconds": dt, "flops": total, "tflops": total / dt / 1e12, "kind": kind,
+            "cores": len(subs), "block_rows": nbr,
+            "sample": f"first {nbr} of {len(nz)} block-rows ({total / 1e9:.1f} GFLOP of nonzero-block "
+                      f"work) at the full n={n}; serial VBR::multiply"
+                      + (f", {len(subs)} independent copies on disjoint block-row ranges" if len(subs) > 1 else "")}
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sparta_b200 import synth
+    N, rowptr, colind = make_matrix(wl)
+    grouping = make_grouping(wl, N, rowptr, colind)
+    # only the sampled block-rows are needed; the fill is cheap enough to do whole
+    v = build_vbr(wl, N, rowptr, colind, grouping)
+    n = wl["n"]
+    Bm = synth.seeded_B(v["cols"], n, seed=2)
+    threads = args.cpu_threads or (os.cpu_count() or 1)
+    per_step = args.cpu_gflop_per_step
+    times, flops, info = [], 0.0, None
+    for i in range(args.warmup + args.steps):
+        info = cpu_reference_sample(v, Bm, n, per_step * threads, threads)
+        if i >= args.warmup:
+            times.append(info["seconds"])
+            flops = info["flops"]
+    t = sum(times)
+    value = flops * len(times) / t / 1e12
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, wl, v),
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+
+METRIC = "VBR SpMM effective TFLOP/s (nonzero-block FLOPs)"
+
+
+def workload_config(args, wl, v):
+    return {"workload": args.workload, "description": wl["desc"], "rows": int(v["rows"]), "cols": int(v["cols"]),
+            "block_col_size": wl["w"], "block_rows": int(v["block_rows"]), "nz_blocks": int(len(v["jab"])),
+            "nztot": int(v["nztot"]), "B_cols": wl["n"], "flop_per_step": 2.0 * v["nztot"] * wl["n"],
+            "l2_policy": "inputs larger than L2 (packed A alone exceeds 126 MB); no flush",
+            "parallelism": f"row-block shards x{args.gpus}, B replicated by one NCCL broadcast"}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"burst": d.get("bf16_tflops"), "sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def read_traffic(workload):
+    """DRAM bytes per launch of the SpMM kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import sparta_b200
+    from sparta_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    lib = sparta_b200.load()
+    if lib.sparta_device_count() < 1:
+        raise SystemExit("bench.py needs a compute-capability 10.x GPU (there is no CPU path); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- host side: matrix -> grouping (rank 0, broadcast) -> VBR
+    t0 = time.perf_counter()
+    N, rowptr, colind = make_matrix(wl)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if world > 1:
+        g = torch.empty(N, dtype=torch.int64, device=dev)
+        if rank == 0:
+            g.copy_(torch.from_numpy(make_grouping(wl, N, rowptr, colind)))
+        dist.broadcast(g, 0)
+        grouping = g.cpu().numpy()
+    else:
+        grouping = make_grouping(wl, N, rowptr, colind)
+    t_block = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    v = build_vbr(wl, N, rowptr, colind, grouping)
+    t_fill = time.perf_counter() - t0
+    n = wl["n"]
+    cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    if rank == 0:
+        log(f"[bench] matrix {N}x{N} nnz={len(colind)} gen {t_gen:.1f}s blocking {t_block:.1f}s fill {t_fill:.1f}s "
+            f"block_rows={v['block_rows']} nz_blocks={len(v['jab'])} nztot={v['nztot']}")
+
+    # ---- device side: A shard resident, B replicated by ONE NCCL broadcast
+    h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
+                                    v["mab"], precision=args.precision, device=local,
+                                    block_row_begin=lo, block_row_end=hi, **tuning_opts(args))
+    Bd = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
+    Bm = None
+    if rank == 0:
+        Bm = synth.seeded_B(v["cols"], n, seed=2)
+        Bd.copy_(torch.from_numpy(Bm))
+    if world > 1:
+        torch.cuda.synchronize()
+        tb0 = time.perf_counter()
+        dist.broadcast(Bd, 0)
+        torch.cuda.synchronize()
+        t_bcast = time.perf_counter() - tb0
+    else:
+        t_bcast = 0.0
+    h.set_B_device(Bd.data_ptr(), v["cols"], n)
+    del Bd
+    st = h.stats()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    my_flops = 2.0 * st["nztot"] * n
+    total_flops = 2.0 * v["nztot"] * n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        h.run_async()
+    h.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    tm0 = sampler.mark()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        h.run_async()
+    ev1.record(stream)
+    ev1.synchronize()
+    torch.cuda.synchronize()
+    tm1 = sampler.mark()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(tm0, tm1) if rank == 0 else None
+    launches = h.stats()["kernel_launches"] - args.warmup
+    t_all = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms_max = float(t_all.item())
+    value = total_flops * args.steps / (ms_max * 1e-3) / 1e12
+
+    # ---- correctness spot check inside the bench (fp64 recomputation of sampled rows)
+    check = spot_check(h, v, lo, hi, n, args.precision, Bm, dist if world > 1 else None, dev, rank)
+
+    # ---- e2e: the one-shot reference-facing call, host buffers in and out (rank-local shard)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist if world > 1 else None, total_flops)
+    h.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        info = cpu_reference_sample(v, Bm, n, args.cpu_gflop, 1)
+        cpu = {"value": info["tflops"], "unit": "TFLOP/s", "cores": 1, "kind": info["kind"],
+               "sample": info["sample"] + f"; {info['seconds']:.1f} s", "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        peaks = read_peaks()
+        per_launch_ms = ms_max / args.steps
+        timed_s = ms_max * 1e-3
+        peak_kind = "burst" if timed_s < 1.0 else "sustained"
+        peak = peaks[peak_kind] * world
+        achieved = total_flops / (per_launch_ms * 1e-3) / 1e12
+        bytes_min = st_bytes_min(v, n, args.precision)
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_launch_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args, wl, v),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": read_traffic(args.workload),
+                         "peak_kind": f"{peak_kind} bf16 cuBLAS, {peaks['source']}" + (f" x{world} GPUs" if world > 1 else ""),
+                         "kernel": "spmm_vbr_sm100", "algorithmic_bytes": bytes_min,
+                         "hbm_frac_of_measured": bytes_min / (per_launch_ms * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world)},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "check": check,
+            "setup": {"blocking_s": t_block, "vbr_fill_s": t_fill, "matrix_gen_s": t_gen,
+                      "a_upload_pack_ms": st["upload_ms"], "b_broadcast_s": t_bcast,
+                      "sched_imbalance": st["sched_imbalance"], "grid": st["grid"], "items": st["items"],
+                      "shard_block_rows": [int(c) for c in cuts]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tuning_opts(args):
+    o = {}
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas"):
+        val = getattr(args, k)
+        if val:
+            o[k] = val
+    return o
+
+
+def st_bytes_min(v, n, precision):
+    """A once + B once (distinct column blocks touched) + C written once."""
+    es = 4 if precision == "tf32" else 2
+    touched = len(np.unique(v["jab"]))
+    return float(v["nztot"] * es + touched * v["block_col_size"] * n * es + v["rows"] * n * 4)
+
+
+def spot_check(h, v, lo, hi, n, precision, Bm, dist, dev, rank):
+    """fp64 recomputation of a few block-rows of this rank's shard from the operands rounded to
+    the kernel's input precision; returns the max relative error (norm of SURVEY 8(c))."""
+    import torch
+    from tests.util import round_to
+    rp, nz, w = v["row_part"], v["nzcount"], v["block_col_size"]
+    if dist is not None:
+        # every rank needs B on the host for the check: fetch it from rank 0
+        Bt = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
+        if rank == 0:
+            Bt.copy_(torch.from_numpy(Bm))
+        dist.broadcast(Bt, 0)
+        Bm = Bt.cpu().numpy()
+    rows_shard = int(rp[hi] - rp[lo])
+    if rows_shard == 0:
+        return {"max_rel_err": 0.0, "block_rows_checked": 0}
+    out = np.zeros((n, rows_shard), dtype=np.float32)
+    h.get_C(out, rows_shard)
+    jab_off = np.concatenate([[0], np.cumsum(nz)])
+    mab_off = np.concatenate([[0], np.cumsum(nz * np.diff(rp) * w)])
+    rng = np.random.default_rng(7 + rank)
+    cand = np.arange(lo, hi)
+    pick = np.unique(np.concatenate([[lo, hi - 1], rng.choice(cand, size=min(3, len(cand)), replace=False)]))
+    Br = round_to(Bm, precision).astype(np.float64)
+    worst, scale = 0.0, 0.0
+    for ib in pick:
+        hgt = int(rp[ib + 1] - rp[ib])
+        acc = np.zeros((n, hgt))
+        for q in range(int(nz[ib])):
+            jb = int(v["jab"][jab_off[ib] + q])
+            blk = v["mab"][mab_off[ib] + q * hgt * w: mab_off[ib] + (q + 1) * hgt * w].reshape(w, hgt)
+            k0, k1 = jb * w, min((jb + 1) * w, v["cols"])
+            acc += Br[:, k0:k1] @ round_to(blk, precision).astype(np.float64)[:k1 - k0]
+        got = out[:, rp[ib] - rp[lo]: rp[ib + 1] - rp[lo]]
+        worst = max(worst, float(np.abs(got - acc).max()))
+        scale = max(scale, float(np.abs(acc).max()))
+    return {"max_rel_err": worst / max(scale, 1e-30), "block_rows_checked": int(len(pick)),
+            "tolerance": 1e-5, "against": "fp64 recomputation from operands rounded to " + precision}
+
+
+def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops):
+    """One-shot sparta_vbr_spmm on this rank's shard: host arrays in, host C out."""
+    import ctypes as C
+    import torch
+    import sparta_b200
+    from sparta_b200 import lib as L
+    lib = sparta_b200.load()
+    rp, nz, w = v["row_part"], v["nzcount"], v["block_col_size"]
+    if dist is not None:
+        Bt = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
+        if rank == 0:
+            Bt.copy_(torch.from_numpy(Bm))
+        dist.broadcast(Bt, 0)
+        Bm = Bt.cpu().numpy()
+        del Bt
+    jab_off = np.concatenate([[0], np.cumsum(nz)])
+    mab_off = np.concatenate([[0], np.cumsum(nz * np.diff(rp) * w)])
+    rows_s = int(rp[hi] - rp[lo])
+    # pinned host buffers, as the contract asks
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    k_rp, a_rp = pin((rp[lo:hi + 1] - rp[lo]).astype(np.int64))
+    k_nz, a_nz = pin(nz[lo:hi].astype(np.int64))
+    k_jab, a_jab = pin(v["jab"][jab_off[lo]:jab_off[hi]].astype(np.int64))
+    k_mab, a_mab = pin(v["mab"][mab_off[lo]:mab_off[hi]])
+    k_B, a_B = pin(Bm)
+    k_C = torch.zeros((n, max(rows_s, 1)), dtype=torch.float32).pin_memory()
+    a_C = k_C.numpy()
+    h2d = a_rp.nbytes + a_nz.nbytes + a_jab.nbytes + a_mab.nbytes + a_B.nbytes
+    d2h = rows_s * n * 4
+    steps = max(1, min(args.steps, args.e2e_steps))
+    dt = C.c_float(0)
+
+    def once():
+        L._check(lib.sparta_vbr_spmm(rows_s, v["cols"], hi - lo, w, L._ptr(a_rp), L._ptr(a_nz), L._ptr(a_jab),
+                                     L._ptr(a_mab), L._ptr(a_B), v["cols"], n, L._ptr(a_C), max(rows_s, 1),
+                                     L.PRECISIONS[args.precision], C.byref(dt)))
+    if rows_s:
+        once()  # warm-up (context, allocator)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if rows_s:
+            once()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    t_all = torch.tensor([sec, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t_all.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_all, op=dist.ReduceOp.SUM)
+        sec = float(tmax[0].item())
+        h2d, d2h = float(t_all[1].item()), float(t_all[2].item())
+    return {"value": total_flops * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * sec / steps,
+            "call": "sparta_vbr_spmm (host VBR + host B -> host C; upload, repack, kernel, download per call; "
+                    "pinned host buffers; wall clock, max over ranks)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rmat16_a5", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-gflop", type=float, default=40.0, help="size of the cpu_baseline sample")
+    ap.add_argument("--cpu-gflop-per-step", type=float, default=8.0,
+                    help="--impl reference: nonzero-block GFLOP per thread-step sample")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas"):
+        ap.add_argument("--" + k.replace("_", "-"), dest=k, type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] warmup < 3 breaks the timing rules; using 3")
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

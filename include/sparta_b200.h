@@ -158,6 +158,25 @@ int sparta_partition_block_rows(int64_t block_rows, const int64_t* row_part,
 
 /* ---- host-side format builders (no GPU needed; bit-exact with the reference) ---- */
 
+/* Row clustering: BlockingEngine::GetGrouping (src/general/blocking.cpp:633-676) on a flat CSR
+ * with strictly ascending columns per row.  Parameters carry the reference CLI meaning
+ * (include/input.h:15-42): algo = -a (0 iterative, 2 fixed, 3 clocked, 4 queue, 5 max-size),
+ * tau = -t, block_col_size = -b, row_block_size = -B, sim_measure = -m (0 Hamming, 1 Jaccard,
+ * 2/3 their probe variants), use_pattern = -p, use_groups = -g, force_fixed_size = -F.
+ * grouping[rows] receives one group id per row, identical to the reference's.  stats (may be
+ * NULL) receives the counters save_blocking_data prints (src/general/utilities.cpp:175-233).
+ * flags bit 0: evaluate Jaccard through the column-list model instead of the block bitmap. */
+typedef struct sparta_blocking_stats {
+  int64_t comparison_counter, merge_counter;
+  float average_merge_tau, average_row_distance;
+  double seconds;
+} sparta_blocking_stats;
+int sparta_host_blocking(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
+                         int32_t algo, float tau, int64_t block_col_size, int64_t row_block_size,
+                         int32_t sim_measure, int32_t use_pattern, int32_t use_groups,
+                         int32_t force_fixed_size, int32_t flags, int64_t* grouping,
+                         sparta_blocking_stats* stats);
+
 /* get_permutation / get_partition (src/general/utilities.cpp:8-43).  perm[n]; part needs
  * n+1 slots, *part_len receives block_rows+1. */
 int sparta_host_permutation(int64_t n, const int64_t* grouping, int64_t* perm);

@@ -9,10 +9,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
 #include "../../include/sparta_b200.h"
+#include "blocking.h"
 #include "host_formats.h"
 #include "pack_kernels.h"
 #include "schedule.h"
@@ -573,6 +575,31 @@ int sparta_partition_block_rows(int64_t block_rows, const int64_t* row_part,
   if (block_rows < 0 || parts <= 0 || !cuts || (block_rows && (!row_part || !nzcount)))
     return fail(SPARTA_ERR_INVALID, "invalid partition request");
   partition_block_rows(block_rows, row_part, nzcount, parts, cuts);
+  return SPARTA_OK;
+}
+
+int sparta_host_blocking(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
+                         int32_t algo, float tau, int64_t block_col_size, int64_t row_block_size,
+                         int32_t sim_measure, int32_t use_pattern, int32_t use_groups,
+                         int32_t force_fixed_size, int32_t flags, int64_t* grouping,
+                         sparta_blocking_stats* stats) {
+  if (rows < 0 || !rowptr || (rows && !grouping) || (rows && rowptr[rows] && !colind))
+    return fail(SPARTA_ERR_INVALID, "NULL CSR or grouping array");
+  BlockingParams p;
+  p.algo = algo; p.tau = tau; p.block_col_size = block_col_size; p.row_block_size = row_block_size;
+  p.sim_measure = sim_measure; p.use_pattern = use_pattern != 0; p.use_groups = use_groups != 0;
+  p.force_fixed_size = force_fixed_size != 0; p.force_list_model = (flags & 1) != 0;
+  BlockingStats st;
+  const auto t0 = std::chrono::steady_clock::now();
+  const char* e = host_blocking(rows, cols, rowptr, colind, p, grouping, &st);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  if (stats) {
+    stats->comparison_counter = st.comparisons;
+    stats->merge_counter = st.merges;
+    stats->average_merge_tau = st.average_merge_tau;
+    stats->average_row_distance = st.average_row_distance;
+    stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
   return SPARTA_OK;
 }
 

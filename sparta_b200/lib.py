@@ -76,6 +76,9 @@ SIGNATURES = {
                                        _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
                                        C.POINTER(C.c_float)]),
     "sparta_partition_block_rows": (C.c_int, [C.c_int64, _vp, _vp, C.c_int32, _vp]),
+    "sparta_host_blocking": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
+                                       C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       _vp, _vp]),
     "sparta_host_permutation": (C.c_int, [C.c_int64, _vp, _vp]),
     "sparta_host_partition": (C.c_int, [C.c_int64, _vp, _vp, C.POINTER(C.c_int64)]),
     "sparta_host_vbr_fill": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int32,
@@ -289,6 +292,29 @@ def _view(ptr, count, dtype):
         return np.zeros(0, dtype=dtype)
     buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr.value)
     return np.frombuffer(buf, dtype=dtype).copy()
+
+
+class BlockingStats(C.Structure):
+    _fields_ = [("comparison_counter", C.c_int64), ("merge_counter", C.c_int64),
+                ("average_merge_tau", C.c_float), ("average_row_distance", C.c_float),
+                ("seconds", C.c_double)]
+
+
+def host_blocking(rows, cols, rowptr, colind, algo=3, tau=0.1, block_col_size=3, row_block_size=3,
+                  sim_measure=1, use_pattern=True, use_group=False, force_fixed_size=False,
+                  list_model=False, return_stats=False):
+    """BlockingEngine::GetGrouping of the reference (src/general/blocking.cpp:633) on a flat CSR;
+    keyword names follow the reference CLI (-a -t -b -B -m -p -g -F)."""
+    rowptr, colind = _i64(rowptr), _i64(colind)
+    grouping = np.zeros(rows, dtype=np.int64)
+    st = BlockingStats()
+    _check(load().sparta_host_blocking(rows, cols, _ptr(rowptr), _ptr(colind), int(algo), float(tau),
+                                       int(block_col_size), int(row_block_size), int(sim_measure),
+                                       int(use_pattern), int(use_group), int(force_fixed_size),
+                                       int(list_model), _ptr(grouping), C.addressof(st)))
+    if return_stats:
+        return grouping, {k: getattr(st, k) for k, _ in st._fields_}
+    return grouping
 
 
 def host_permutation(grouping):

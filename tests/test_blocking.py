@@ -1,0 +1,114 @@
+"""The product's row clustering (sparta_b200/csrc/blocking.cpp, through the C ABI) against
+  * the golden groupings captured from the compiled reference (tests/golden/*.json),
+  * the oracle restatement, and
+  * the unmodified reference build (oracle/_ref, where present)
+element for element, including the merge statistics the reference prints in its CSV.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from sparta_b200 import lib as L
+from sparta_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+with open(os.path.join(GOLDEN, "reference_vectors.json")) as f:
+    VECTORS = json.load(f)
+
+
+def product_grouping(rec_or_res, flags, **kw):
+    """Run the product blocking on the (already -r reordered) CSR the reference produced."""
+    f = dict(a=3, b=3, B=3, t=0.1, m=1, p=1, g=0, F=0)
+    f.update(flags)
+    rowptr = np.asarray(rec_or_res["csr_rowptr"], dtype=np.int64)
+    colind = np.asarray(rec_or_res["csr_colind"], dtype=np.int64)
+    return L.host_blocking(int(rec_or_res["csr_rows"]), int(rec_or_res["csr_cols"]), rowptr, colind,
+                           algo=f["a"], tau=f["t"], block_col_size=f["b"], row_block_size=f["B"],
+                           sim_measure=f["m"], use_pattern=bool(f["p"]), use_group=bool(f["g"]),
+                           force_fixed_size=bool(f["F"]), return_stats=True, **kw)
+
+
+def same_float(a, b):
+    a, b = np.float32(a), np.float32(b)
+    return a == b or (a != a and b != b)
+
+
+@pytest.mark.parametrize("idx", range(len(VECTORS)))
+@pytest.mark.parametrize("list_model", [False, True])
+def test_grouping_matches_golden(lib, idx, list_model):
+    rec = VECTORS[idx]
+    g, st = product_grouping(rec, rec["flags"], list_model=list_model)
+    assert g.tolist() == rec["grouping"]
+    assert st["comparison_counter"] == rec["comparison_counter"]
+    assert st["merge_counter"] == rec["merge_counter"]
+    assert same_float(st["average_merge_tau"], rec["average_merge_tau"] if rec["average_merge_tau"] is not None else np.nan)
+    assert same_float(st["average_row_distance"],
+                      rec["average_row_distance"] if rec["average_row_distance"] is not None else np.nan)
+
+
+FLAG_SETS = [
+    dict(a=3, b=8, t=0.6), dict(a=4, b=8, t=0.6), dict(a=5, b=8, B=8, t=0.6), dict(a=0, b=8, t=0.5),
+    dict(a=5, b=16, B=32, t=0.3), dict(a=5, b=8, B=7, t=0.9), dict(a=2, b=8, B=8, F=1),
+    dict(a=3, b=8, B=8, t=0.5, F=1), dict(a=3, b=4, t=0.4, m=0), dict(a=4, b=4, t=3.0, m=0),
+    dict(a=5, b=8, B=8, t=2.0, m=2), dict(a=3, b=8, t=0.5, m=3), dict(a=4, b=8, t=1.0), dict(a=4, b=8, t=0.0),
+    dict(a=5, b=8, B=8, t=0.6, g=1), dict(a=3, b=8, t=0.6, g=1, p=0), dict(a=5, b=64, B=64, t=0.6),
+    dict(a=5, b=1, B=16, t=0.7), dict(a=4, b=3, t=0.8, g=1), dict(a=5, b=8, B=8, t=1.0),
+]
+
+
+def matrices(tmp_path):
+    r, c = synth.rmat_edges(10, 14000, seed=3)
+    r, c = synth.pin_shape(r, c, 1024, 1024)
+    p1 = str(tmp_path / "rmat.el")
+    synth.write_el(p1, r, c)
+    # sparse ER with many empty rows (the empty-row / empty-pattern corners of the distances)
+    r, c = synth.er_edges(700, 650, 0.004, seed=9)
+    p2 = str(tmp_path / "er.el")
+    synth.write_el(p2, r, c)
+    return [p1, p2]
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS, ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()))
+def test_grouping_matches_oracle_and_reference(lib, oracle, tmp_path, flags):
+    from oracle.oracle_py import Reference
+    ref = Reference() if Reference.available() else None
+    for path in matrices(tmp_path):
+        res = oracle.run(path, P=1, fill=False, **flags)
+        g, st = product_grouping(res, flags)
+        assert np.array_equal(g, res["grouping"]), path
+        assert st["comparison_counter"] == res["comparison_counter"]
+        assert st["merge_counter"] == res["merge_counter"]
+        assert same_float(st["average_merge_tau"], res["average_merge_tau"])
+        assert same_float(st["average_row_distance"], res["average_row_distance"])
+        if flags.get("m", 1) == 1:
+            g2, _ = product_grouping(res, flags, list_model=True)
+            assert np.array_equal(g2, g)
+        # -m 2 (HammingDistanceGroupOPENMP) dereferences vector::end() when a probe runs off the
+        # pattern (blocking.cpp:773-774): heap garbage decides, so only the restatement's reading
+        # ("counts as different") can be pinned for it.
+        if ref is not None and flags.get("m", 1) != 2:
+            rr = ref.run(path, fill=False, P=1, **flags)
+            assert np.array_equal(g, rr["grouping"]), path
+
+
+def test_blocking_then_fill_equals_reference_vbr(lib, oracle, tmp_path):
+    """grouping -> VBR::fill_from_CSR_inplace through the product only, vs the oracle's arrays."""
+    path = matrices(tmp_path)[0]
+    flags = dict(a=5, b=16, B=16, t=0.6)
+    res = oracle.run(path, P=1, **flags)
+    g, _ = product_grouping(res, flags)
+    v = L.host_vbr_fill(res["csr_rows"], res["csr_cols"], res["csr_rowptr"], res["csr_colind"], None, g,
+                        16, 16, False, pattern_only=True)
+    for k in ("row_part", "nzcount", "jab", "mab"):
+        assert np.array_equal(v[k], res[k]), k
+
+
+def test_invalid_arguments(lib):
+    rowptr = np.array([0, 2, 3], dtype=np.int64)
+    with pytest.raises(L.SpartaError):
+        L.host_blocking(2, 4, rowptr, np.array([1, 0, 2]), algo=3, block_col_size=2)   # unsorted row
+    with pytest.raises(L.SpartaError):
+        L.host_blocking(2, 4, rowptr, np.array([0, 1, 2]), algo=1, block_col_size=2)   # -a 1 unsupported
+    with pytest.raises(L.SpartaError):
+        L.host_blocking(2, 4, rowptr, np.array([0, 1, 9]), algo=3, block_col_size=2)   # column out of range
