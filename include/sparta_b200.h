@@ -52,12 +52,15 @@ typedef struct sparta_options {
   int32_t c_layout;      /* same default as b_layout */
   int32_t accumulate;    /* 0: C := A*B (default) ; 1: C += A*B */
   int32_t seg_rows;      /* max rows per MMA segment, multiple of 16 <= 256 (default 64) */
-  int32_t acc_cols;      /* TMEM columns per accumulator stage: 256 (default) or 512 */
+  int32_t acc_cols;      /* TMEM columns per accumulator stage: 512 (default, one stage) or 256 (two) */
   int32_t panel_stages;  /* smem pipeline depth, 2..8 (default 4) */
   int32_t num_ctas;      /* persistent grid size (default: SM count) */
   int64_t block_row_begin; /* shard: first block-row (default 0) */
   int64_t block_row_end;   /* shard: one past the last block-row (default: all) */
-  int32_t reserved[8];
+  int32_t cta_pair;      /* 0/2: CTA pairs, tcgen05 cta_group::2, 256-column tiles (default); 1: single CTAs */
+  int32_t row_order;     /* 0/2: super-rows group block-rows of similar block count (default); 1: input order */
+  int32_t l2_slab_mb;    /* B columns kept L2-resident per pass, in MiB of B (default 80) */
+  int32_t reserved[5];
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */
@@ -71,11 +74,13 @@ typedef struct sparta_stats {
   int64_t a_packed_bytes;  /* device bytes of the packed A images */
   int64_t b_bytes;         /* device bytes of the converted B operand */
   int64_t c_bytes;         /* device bytes of C */
-  int32_t grid;            /* CTAs launched by sparta_run */
+  int32_t grid;            /* CTAs launched by sparta_run (2 per worker in pair mode) */
   int32_t smem_bytes;      /* dynamic shared memory per CTA */
   double  sched_imbalance; /* modelled max/mean CTA load */
   double  upload_ms;       /* host->device + packing time of the last create/set_B */
   int64_t kernel_launches; /* sm_100a SpMM launches issued through this handle */
+  int32_t team;            /* workers walking one super-row side by side (column tiles per L2 pass) */
+  int32_t cta_pair;        /* 1 when the handle runs CTA pairs */
 } sparta_stats;
 
 const char* sparta_last_error(void);

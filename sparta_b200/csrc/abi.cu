@@ -83,7 +83,8 @@ static void resolve_options(const sparta_options* in, sparta_options* o) {
     memcpy(o, in, std::min(sz, sizeof(*o)));
   }
   if (o->seg_rows == 0) o->seg_rows = 64;
-  if (o->acc_cols == 0) o->acc_cols = 256;
+  if (o->acc_cols == 0) o->acc_cols = 512;
+  if (o->l2_slab_mb <= 0) o->l2_slab_mb = 80;
   if (o->panel_stages == 0) o->panel_stages = 4;
 }
 
@@ -211,6 +212,9 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->sopt.seg_rows = o.seg_rows;
   h->sopt.acc_cols = o.acc_cols;
   h->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : sms;
+  h->sopt.pair = o.cta_pair != 1;
+  h->sopt.sort_rows = o.row_order != 1;
+  h->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
   h->panel_stages = o.panel_stages;
   h->a_ring_bytes = ring_bytes_for(o.panel_stages);
   h->accumulate = o.accumulate ? 1 : 0;
@@ -384,7 +388,7 @@ int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on
   if (e != cudaSuccess) return fail_cuda(e, "B conversion");
 
   if (n != h->n) {
-    const char* serr = build_assignment(h->st, h->sopt, n, &h->as);
+    const char* serr = build_assignment(h->st, h->sopt, n, h->cols, &h->as);
     if (*serr) return fail(SPARTA_ERR_INVALID, serr);
     cudaFree(h->d_items); cudaFree(h->d_cta_ptr); cudaFree(h->d_cta_items);
     h->d_items = nullptr; h->d_cta_ptr = nullptr; h->d_cta_items = nullptr;
@@ -457,7 +461,9 @@ static int launch(sparta_handle* h) {
   // tcgen05 instruction descriptor (kind::f16 / kind::tf32): D fp32 at [4,6), A/B
   // format at [7,10)/[10,13) (0 f16, 1 bf16, 2 tf32), both K-major, M=128 at [24,29)
   const uint32_t fmt = h->sopt.precision == PREC_BF16 ? 1u : (h->sopt.precision == PREC_FP16 ? 0u : 2u);
-  p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
+  const uint32_t mma_m = h->st.pair ? 256u : 128u;
+  p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((mma_m >> 4) << 24);
+  p.pair = h->st.pair;
   p.kind_tf32 = h->sopt.precision == PREC_TF32;
   p.panel_stages = h->panel_stages;
   p.a_ring_bytes = h->a_ring_bytes;
@@ -512,6 +518,8 @@ static void fill_stats(const Structure& st, const Assignment& as, int64_t cols, 
   s->grid = as.grid;
   s->smem_bytes = spmm_smem_bytes(panel_stages, a_ring_bytes);
   s->sched_imbalance = as.mean_cta_cost > 0 ? as.max_cta_cost / as.mean_cta_cost : 1.0;
+  s->team = as.team;
+  s->cta_pair = st.pair;
 }
 
 int sparta_get_stats(sparta_handle* h, sparta_stats* out) {
@@ -693,11 +701,14 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
   p->sopt.seg_rows = o.seg_rows;
   p->sopt.acc_cols = o.acc_cols;
   p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  p->sopt.pair = o.cta_pair != 1;
+  p->sopt.sort_rows = o.row_order != 1;
+  p->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
   p->cols = cols; p->block_rows = br.count(); p->n = n;
   p->panel_stages = o.panel_stages;
   p->a_ring_bytes = ring_bytes_for(o.panel_stages);
   e = build_structure(br, p->sopt, &p->st);
-  if (!*e) e = build_assignment(p->st, p->sopt, n, &p->as);
+  if (!*e) e = build_assignment(p->st, p->sopt, n, cols, &p->as);
   if (*e) { delete p; return fail(SPARTA_ERR_INVALID, e); }
   *out = p;
   return SPARTA_OK;

@@ -17,6 +17,7 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Structure* out) {
   Structure& st = *out;
   st = Structure();
+  st.pair = opt.pair ? 1 : 0;
   if (br.w <= 0) return "column block size must be positive";
   if (opt.seg_rows < 16 || opt.seg_rows > 256 || opt.seg_rows % 16) return "seg_rows must be a multiple of 16 in [16,256]";
   if (opt.acc_cols != 256 && opt.acc_cols != 512) return "acc_cols must be 256 or 512";
@@ -25,12 +26,25 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
   const int katom = 128 / esize;    // k elements per 128-byte swizzle row
   const int kstep = 32 / esize;     // k elements per MMA (K = 16 for 16-bit, 8 for tf32)
   const int kalign = 16 / esize;    // TMA needs a 16-byte aligned start along k
+  const int nshare = st.pair ? 2 : 1;
+
+  // 0. order of the block-rows.  C rows are written wherever row_part says, so the order in
+  //    which block-rows are grouped into super-rows is free: putting block-rows with similar
+  //    nonzero-block counts together makes their column-block lists overlap (on R-MAT the
+  //    dense rows are near-supersets of each other), so a B panel feeds more MMA rows.
+  const int64_t nb = br.count();
+  std::vector<int64_t> order(nb);
+  for (int64_t b = 0; b < nb; ++b) order[b] = b;
+  if (opt.sort_rows)
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      return br.ptr[a + 1] - br.ptr[a] > br.ptr[b + 1] - br.ptr[b];
+    });
 
   // 1. segments, tagged with their block-row and row offset inside it
   struct SegSrc { int64_t b; int64_t row_off; };
   std::vector<SegSrc> seg_src;
-  const int64_t nb = br.count();
-  for (int64_t b = 0; b < nb; ++b) {
+  for (int64_t oi = 0; oi < nb; ++oi) {
+    const int64_t b = order[oi];
     const int64_t H = br.height[b];
     const int64_t nblk = br.ptr[b + 1] - br.ptr[b];
     st.n_blocks += nblk;  // zero-height block-rows keep their (empty) blocks in the count
@@ -53,6 +67,8 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
   const size_t nseg = st.segs.size();
   size_t s0 = 0;
   std::vector<std::pair<int64_t, int>> merged;  // (jb, member)
+  int32_t cols_of[kMaxMembers + 1];
+  const int64_t* slot_of[kMaxMembers];          // per member: position of jb inside its block-row
   while (s0 < nseg) {
     SuperRow sr{};
     sr.seg_begin = static_cast<int32_t>(s0);
@@ -61,9 +77,11 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
     while (s1 < nseg && (s1 - s0) < static_cast<size_t>(kMaxMembers) &&
            cols + st.segs[s1].h_pad <= opt.acc_cols) {
       st.segs[s1].tmem_col = cols;
+      cols_of[s1 - s0] = cols;
       cols += st.segs[s1].h_pad;
       ++s1;
     }
+    cols_of[s1 - s0] = cols;
     sr.seg_count = static_cast<int32_t>(s1 - s0);
     sr.n_cols = cols;
     sr.chunk_begin = static_cast<int32_t>(st.chunks.size());
@@ -76,16 +94,22 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
         merged.emplace_back(br.col[q], static_cast<int>(s - s0));
     }
     std::sort(merged.begin(), merged.end());
-    double cost = 12.0 * cols;  // epilogue drain
+    double cost = 200.0 + 6.0 * cols;  // pipeline fill + epilogue drain
     size_t i = 0;
     while (i < merged.size()) {
       const int64_t jb = merged[i].first;
       size_t i1 = i;
       uint32_t mask = 0;
       while (i1 < merged.size() && merged[i1].first == jb) {
-        mask |= 1u << merged[i1].second;
+        const int m = merged[i1].second;
+        mask |= 1u << m;
+        const int64_t b = seg_src[s0 + m].b;
+        const int64_t* cb = br.col.data() + br.ptr[b];
+        slot_of[m] = cb + (std::lower_bound(cb, br.col.data() + br.ptr[b + 1], jb) - cb);
         ++i1;
       }
+      uint32_t rows_present = 0;
+      for (size_t t = i; t < i1; ++t) rows_present += st.segs[s0 + merged[t].second].h_pad;
       // K slabs of this column block: start at the 16-byte aligned k at or below jb*w
       const int64_t kblk = jb * br.w;
       const int64_t ka = kblk / kalign * kalign;
@@ -102,35 +126,47 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
         ch.ksteps = (k_used + kstep - 1) / kstep;
         if ((st.a_bytes >> 4) > UINT32_MAX) return "packed A exceeds 64 GiB";
         ch.a_off16 = static_cast<uint32_t>(st.a_bytes >> 4);
-        uint32_t bytes = 0;
-        for (size_t t = i; t < i1; ++t) {
-          const int m = merged[t].second;
-          const size_t s = s0 + m;
-          const int64_t b = seg_src[s].b;
-          // position of block jb inside block-row b
-          const int64_t* cb = br.col.data() + br.ptr[b];
-          const int64_t* ce = br.col.data() + br.ptr[b + 1];
-          const int64_t q = br.ptr[b] + (std::lower_bound(cb, ce, jb) - cb);
-          PackJob job;
-          job.src_rs = br.rs[b];
-          job.src_ks = br.ks[b];
-          job.src_base = br.src[q] + seg_src[s].row_off * job.src_rs;
-          job.h = st.segs[s].h;
-          job.h_pad = st.segs[s].h_pad;
-          job.k_lo = static_cast<int32_t>(k_lo);
-          job.k_w = static_cast<int32_t>(br.w);
-          job.pad_[0] = job.pad_[1] = job.pad_[2] = 0;
-          job.dst_off16 = static_cast<uint32_t>((st.a_bytes + bytes) >> 4);
-          st.jobs.push_back(job);
-          bytes += static_cast<uint32_t>(job.h_pad) * 128u;
-        }
+        const uint32_t bytes = rows_present * 128u;
+        const uint32_t share = bytes / nshare;       // bytes each CTA stages for this chunk
+        uint32_t cursor[2] = {0, 0};                 // write position inside each CTA's share
+        const uint64_t chunk_base = st.a_bytes;
+        // Images are laid out run by run (the unit of one MMA); in pair mode the first half of a
+        // run's rows goes to CTA 0's share and the second half to CTA 1's (cta_group::2 reads
+        // N/2 rows of the N operand from each CTA).
+        for_each_run(mask, cols_of, [&](int mb, int me, int N) {
+          const int half = N / nshare;
+          for (int m = mb; m < me; ++m) {
+            const size_t s = s0 + m;
+            const int64_t b = seg_src[s].b;
+            const int64_t q = slot_of[m] - br.col.data();
+            const int lo = cols_of[m] - cols_of[mb];            // member rows inside the run
+            const int hi = lo + st.segs[s].h_pad;
+            for (int cta = 0; cta < nshare; ++cta) {
+              const int r0 = std::max(lo, cta * half), r1 = std::min(hi, (cta + 1) * half);
+              if (r0 >= r1) continue;
+              PackJob job;
+              job.src_rs = br.rs[b];
+              job.src_ks = br.ks[b];
+              job.src_base = br.src[q] + (seg_src[s].row_off + (r0 - lo)) * job.src_rs;
+              job.h = std::max(0, std::min(st.segs[s].h - (r0 - lo), r1 - r0));
+              job.h_pad = r1 - r0;
+              job.k_lo = static_cast<int32_t>(k_lo);
+              job.k_w = static_cast<int32_t>(br.w);
+              job.pad_[0] = job.pad_[1] = job.pad_[2] = 0;
+              job.dst_off16 = static_cast<uint32_t>((chunk_base + cta * share + cursor[cta]) >> 4);
+              st.jobs.push_back(job);
+              cursor[cta] += static_cast<uint32_t>(r1 - r0) * 128u;
+            }
+          }
+        });
         ch.a_bytes = bytes;
         st.a_bytes += bytes;
-        st.max_chunk_bytes = std::max(st.max_chunk_bytes, bytes);
+        st.max_chunk_bytes = std::max(st.max_chunk_bytes, share);
         st.chunks.push_back(ch);
-        const double tensor = ch.ksteps * (bytes / 128.0) * 0.5;  // N/2 cycles per MMA at M=128
-        const double memory = (kPanelBytes + bytes) / 48.0;
-        cost += std::max(tensor, memory) + 40.0;
+        // modelled cycles per CTA: tensor pipe N/2 per K step; L2 -> smem at ~40 B/cycle/SM
+        const double tensor = ch.ksteps * (rows_present * 0.5);
+        const double memory = (kPanelBytes + share) / 40.0;
+        cost += std::max(tensor, memory) + 30.0;
       }
       i = i1;
     }
@@ -143,41 +179,71 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
   return "";
 }
 
+// Work order and static assignment.
+//
+// Columns of B are processed in GROUPS of `group_tiles` column tiles whose B slab
+// (cols x group width) stays L2-resident while every super-row streams its A images past it,
+// so HBM sees B about once and A once per group instead of once per column tile.  Inside a
+// group the workers form TEAMS of `team` = group_tiles workers: a team walks the same sequence
+// of super-rows side by side, one column tile each, so a super-row's A images are fetched from
+// HBM by whichever member gets there first and hit in L2 for the others.  Super-rows are
+// list-scheduled, heaviest first, onto the team that frees up first (modelled cost).
 const char* build_assignment(const Structure& st, const ScheduleOptions& opt, int64_t n,
-                             Assignment* out) {
+                             int64_t k_total, Assignment* out) {
   Assignment& as = *out;
   as = Assignment();
-  if (n <= 0 || n > INT32_MAX - kTileJ) return "invalid number of B columns";
-  const int64_t tiles = (n + kTileJ - 1) / kTileJ;
-  const int64_t n_items = static_cast<int64_t>(st.srows.size()) * tiles;
+  const int tile = st.pair ? 2 * kTileJ : kTileJ;
+  if (n <= 0 || n > INT32_MAX - tile) return "invalid number of B columns";
+  const int64_t tiles = (n + tile - 1) / tile;
+  const int64_t n_srows = static_cast<int64_t>(st.srows.size());
+  const int64_t n_items = n_srows * tiles;
   if (n_items > INT32_MAX) return "too many work items";
-  as.items.reserve(n_items);
-  std::vector<double> cost;
-  cost.reserve(n_items);
-  for (size_t s = 0; s < st.srows.size(); ++s)
-    for (int64_t t = 0; t < tiles; ++t) {
-      as.items.push_back(Item{static_cast<int32_t>(s), static_cast<int32_t>(t * kTileJ)});
-      cost.push_back(st.srow_cost[s]);
-    }
-  as.grid = static_cast<int>(std::min<int64_t>(opt.num_ctas, n_items));
-  as.cta_ptr.assign(as.grid + 1, 0);
-  if (as.grid == 0) return "";
+  int workers = std::max(1, opt.num_ctas / (st.pair ? 2 : 1));
+  workers = static_cast<int>(std::min<int64_t>(workers, std::max<int64_t>(n_items, 1)));
+  as.workers = n_items ? workers : 0;
+  as.grid = as.workers * (st.pair ? 2 : 1);
+  as.cta_ptr.assign(as.workers + 1, 0);
+  if (n_items == 0) return "";
 
-  // longest-processing-time-first onto the persistent CTAs
-  std::vector<int32_t> order(n_items);
-  for (int64_t i = 0; i < n_items; ++i) order[i] = static_cast<int32_t>(i);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
+  // column tiles per group: the largest divisor of the worker count whose slab fits
+  const double tile_bytes = static_cast<double>(k_total) * tile * prec_esize(opt.precision);
+  int64_t fit = std::max<int64_t>(1, static_cast<int64_t>(opt.l2_slab_bytes / std::max(tile_bytes, 1.0)));
+  fit = std::min(fit, tiles);
+  int team = 1;
+  for (int t = 1; t <= workers && t <= fit; ++t)
+    if (workers % t == 0) team = t;
+  if (fit >= tiles && tiles <= workers) {
+    // the whole of B fits: one group; teams as wide as the tile count allows
+    team = 1;
+    for (int t = 1; t <= tiles; ++t)
+      if (workers % t == 0 && tiles % t == 0) team = t;
+  }
+  as.team = team;
+  as.group_tiles = team;
+  const int n_teams = workers / team;
+
+  std::vector<int32_t> by_cost(n_srows);
+  for (int64_t s = 0; s < n_srows; ++s) by_cost[s] = static_cast<int32_t>(s);
+  std::stable_sort(by_cost.begin(), by_cost.end(),
+                   [&](int32_t a, int32_t b) { return st.srow_cost[a] > st.srow_cost[b]; });
+
   typedef std::pair<double, int> Load;
   std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-  for (int c = 0; c < as.grid; ++c) heap.push(Load(0.0, c));
-  std::vector<std::vector<int32_t>> per_cta(as.grid);
-  for (int32_t id : order) {
-    Load l = heap.top();
-    heap.pop();
-    per_cta[l.second].push_back(id);
-    l.first += cost[id];
-    heap.push(l);
+  for (int t = 0; t < n_teams; ++t) heap.push(Load(0.0, t));
+  std::vector<std::vector<int32_t>> per_worker(workers);
+  as.items.reserve(n_items);
+  for (int64_t t0 = 0; t0 < tiles; t0 += team) {
+    const int in_group = static_cast<int>(std::min<int64_t>(team, tiles - t0));
+    for (int32_t s : by_cost) {
+      Load l = heap.top();
+      heap.pop();
+      for (int m = 0; m < in_group; ++m) {
+        per_worker[l.second * team + m].push_back(static_cast<int32_t>(as.items.size()));
+        as.items.push_back(Item{s, static_cast<int32_t>((t0 + m) * tile)});
+      }
+      l.first += st.srow_cost[s];
+      heap.push(l);
+    }
   }
   double total = 0;
   while (!heap.empty()) {
@@ -185,13 +251,13 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
     total += heap.top().first;
     heap.pop();
   }
-  as.mean_cta_cost = total / as.grid;
+  as.mean_cta_cost = total / n_teams;
   as.cta_items.reserve(n_items);
-  for (int c = 0; c < as.grid; ++c) {
+  for (int c = 0; c < workers; ++c) {
     as.cta_ptr[c] = static_cast<int32_t>(as.cta_items.size());
-    as.cta_items.insert(as.cta_items.end(), per_cta[c].begin(), per_cta[c].end());
+    as.cta_items.insert(as.cta_items.end(), per_worker[c].begin(), per_worker[c].end());
   }
-  as.cta_ptr[as.grid] = static_cast<int32_t>(as.cta_items.size());
+  as.cta_ptr[workers] = static_cast<int32_t>(as.cta_items.size());
   return "";
 }
 

@@ -24,8 +24,11 @@ struct BlockRows {
 struct ScheduleOptions {
   int precision = PREC_BF16;
   int seg_rows = 64;       // max rows per segment (multiple of 16, <= 256)
-  int acc_cols = 256;      // TMEM columns per accumulator stage: 256 (2 stages) or 512 (1)
+  int acc_cols = 512;      // TMEM columns per accumulator stage: 256 (2 stages) or 512 (1)
   int num_ctas = 148;      // persistent grid size upper bound
+  int pair = 1;            // 1: two CTAs (one TPC) share a super-row through tcgen05 cta_group::2
+  int sort_rows = 1;       // 1: group block-rows of similar nonzero-block count into super-rows
+  int64_t l2_slab_bytes = 64ll << 20;  // B columns kept L2-resident at a time (see build_assignment)
 };
 
 struct Structure {           // independent of the number of B columns
@@ -38,21 +41,49 @@ struct Structure {           // independent of the number of B columns
   int64_t  nztot = 0;                // sum over blocks of h*w (the reference's VBR::nztot)
   int64_t  n_blocks = 0;
   int64_t  rows = 0;                 // C rows covered by the shard
-  uint32_t max_chunk_bytes = 0;
+  uint32_t max_chunk_bytes = 0;      // largest per-CTA chunk (what must fit in the smem ring)
+  int pair = 0;
 };
+
+// Decomposition of a chunk's member mask into MMA runs: maximal groups of consecutive present
+// members whose accumulators are adjacent and span at most 256 columns.  The kernel issues one
+// MMA (per K step) per run; in pair mode the run's rows are split half/half between the CTAs.
+// cols[m] = first accumulator column of member m, cols[count] = total.  fn(m_begin, m_end, N).
+template <class F>
+inline void for_each_run(uint32_t mask, const int32_t* cols, F fn) {
+  while (mask) {
+    const int m0 = __builtin_ctz(mask);
+    const uint32_t inv = ~(mask >> m0);
+    const int len = inv ? __builtin_ctz(inv) : (32 - m0);
+    const int mend = m0 + len;
+    int m = m0;
+    while (m < mend) {
+      const int mstart = m;
+      const int col0 = cols[mstart];
+      ++m;
+      while (m < mend && cols[m + 1] - col0 <= 256) ++m;
+      fn(mstart, m, cols[m] - col0);
+    }
+    const uint32_t run = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
+    mask &= ~(run << m0);
+  }
+}
 
 struct Assignment {          // depends on n (columns of B) and the grid
   std::vector<Item>    items;
-  std::vector<int32_t> cta_ptr;
+  std::vector<int32_t> cta_ptr;     // per worker (a CTA, or a CTA pair in pair mode)
   std::vector<int32_t> cta_items;
-  int grid = 0;
+  int grid = 0;                     // CTAs to launch (2 x workers in pair mode)
+  int workers = 0;
+  int team = 1;                     // workers walking the same super-row sequence side by side
+  int group_tiles = 1;              // column tiles per L2-resident group
   double max_cta_cost = 0, mean_cta_cost = 0;
 };
 
 // Returns "" on success, otherwise a static error string.
 const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Structure* out);
 const char* build_assignment(const Structure& st, const ScheduleOptions& opt, int64_t n,
-                             Assignment* out);
+                             int64_t k_total, Assignment* out);
 
 // Contiguous block-row ranges balanced on nonzero-block area (sum h*w), the
 // partition SURVEY 8(e) prescribes for multi-GPU sharding.  cuts has parts+1 entries.

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "spmm_kernel.h"
 
 namespace sparta {
@@ -55,6 +56,37 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// acquire at cluster scope: the observed arrival may come from the peer CTA of a pair
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -65,7 +97,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_cluster(bar, parity)) {
     if (((++spins) & 0x3FF) == 0 && global_timer_ns() - t0 > 5000000000ull) {
       printf("sparta spmm: mbarrier wait timed out (cta %d thread %d tag %d parity %u)\n",
              blockIdx.x, threadIdx.x, tag, parity);
@@ -74,7 +106,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int t
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait_cluster(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
 
@@ -101,18 +133,41 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// Completion of all previously issued MMAs arrives on `bar`; in pair mode on the barrier at
+// the same offset in BOTH CTAs (the peer's producer / epilogue wait on their own copy).
+template <bool kPair>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   bar)
-               : "memory");
+  if constexpr (kPair) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+        " [%0], %1;" ::"r"(bar),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     bar)
+                 : "memory");
+  }
 }
-template <bool kTf32>
+template <bool kTf32, bool kPair>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                        uint32_t idesc) {
-  if constexpr (kTf32) {
+  if constexpr (kTf32 && kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
+        : "memory");
+  } else if constexpr (kTf32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
+        : "memory");
+  } else if constexpr (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u)
         : "memory");
   } else {
@@ -157,6 +212,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+
 struct StageMeta {
   uint32_t mask;
   int32_t  ksteps;
@@ -165,7 +221,16 @@ struct StageMeta {
 };
 
 // ------------------------------------------------------------------ kernel
-template <bool kTf32>
+// kPair = false: one CTA owns a (super-row, 128-column tile) item; MMAs are cta_group::1, M = 128.
+// kPair = true : the two CTAs of a cluster (one TPC) own a (super-row, 256-column tile) item.
+//   Each CTA stages ITS 128 columns of the B panel and HALF of the rows of every A image run;
+//   the leader CTA (cluster rank 0) issues cta_group::2 MMAs with M = 256 that read both
+//   CTAs' shared memory, and each CTA's TMEM receives the accumulators of its own 128 columns.
+//   Per unit of tensor work an SM therefore pulls half as many A bytes out of L2.
+//   Cross-CTA signalling: the peer forwards "my stage is full" to the leader with a remote
+//   mbarrier arrive; stage release and accumulator-ready are tcgen05.commit multicasts;
+//   "accumulator drained" of the peer's epilogue warps is a remote arrive on the leader.
+template <bool kTf32, bool kPair>
 __global__ void __launch_bounds__(kSpmmThreads, 1)
 spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -179,54 +244,68 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   const uint32_t a_ring = base + P * kPanelBytes;
   uint8_t* ctrl = smem + P * kPanelBytes + p.a_ring_bytes;
   const uint32_t ctrl_u = a_ring + p.a_ring_bytes;
-  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | meta[8] |
+  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | peer_full[8] | meta[8] |
   //              tmem_ptr | starts[8] | cols[33]
   const uint32_t bar_full = ctrl_u;
   const uint32_t bar_empty = ctrl_u + 64;
   const uint32_t bar_acc_full = ctrl_u + 128;
   const uint32_t bar_acc_empty = ctrl_u + 144;
-  StageMeta* meta = reinterpret_cast<StageMeta*>(ctrl + 160);
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(ctrl + 288);
-  uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 320);
-  int32_t* s_col = reinterpret_cast<int32_t*>(ctrl + 352);  // 33 ints
+  const uint32_t bar_peer_full = ctrl_u + 160;
+  StageMeta* meta = reinterpret_cast<StageMeta*>(ctrl + 224);
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(ctrl + 352);
+  uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 384);
+  int32_t* s_col = reinterpret_cast<int32_t*>(ctrl + 416);  // 33 ints
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader
+  const int worker = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  constexpr int kShare = kPair ? 1 : 0;                   // per-CTA bytes = chunk bytes >> kShare
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_peer_full + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+      mbar_init(bar_acc_empty + 8 * s, kPair ? 8 : 4);  // one arrival per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(const_cast<uint32_t*>(tmem_ptr_s))),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_ptr_s))),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_ptr_s))),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const int it_begin = p.cta_ptr[blockIdx.x];
-  const int it_end = p.cta_ptr[blockIdx.x + 1];
+  const int it_begin = p.cta_ptr[worker];
+  const int it_end = p.cta_ptr[worker + 1];
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
+    // ===================== TMA producer (one thread, every CTA) =====================
     if (lane == 0) {
       const uint32_t RB = static_cast<uint32_t>(p.a_ring_bytes);
       uint32_t iss = 0, rel = 0, head = 0;
       for (int it = it_begin; it < it_end; ++it) {
         const Item item = p.items[p.cta_items[it]];
         const SuperRow sr = p.srows[item.srow];
+        const int j0 = item.j0 + static_cast<int>(rank) * kTileJ;
         for (int c = 0; c < sr.chunk_count; ++c) {
           const Chunk ch = p.chunks[sr.chunk_begin + c];
           // stage slot: the use that last occupied it must have been released
@@ -234,8 +313,9 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             mbar_wait(bar_empty + 8 * (rel % P), (rel / P) & 1, 1);
             ++rel;
           }
-          // contiguous space in the A ring (FIFO release order)
-          const uint32_t bytes = ch.a_bytes;
+          // contiguous space in the A ring (FIFO release order).  The offsets depend only on
+          // the sequence of sizes, so both CTAs of a pair place every chunk at the same offset.
+          const uint32_t bytes = ch.a_bytes >> kShare;
           uint32_t off;
           for (;;) {
             if (rel == iss) { off = 0; break; }
@@ -258,8 +338,9 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
           meta[s].a_off = off;
           const uint32_t full = bar_full + 8 * s;
           mbar_arrive_expect_tx(full, kPanelBytes + bytes);
-          tma_load_2d(panels + s * kPanelBytes, &tmap_b, ch.k0, item.j0, full);
-          const uint8_t* src = p.a_packed + static_cast<size_t>(ch.a_off16) * 16;
+          tma_load_2d(panels + s * kPanelBytes, &tmap_b, ch.k0, j0, full);
+          const uint8_t* src = p.a_packed + static_cast<size_t>(ch.a_off16) * 16 +
+                               static_cast<size_t>(rank) * bytes;
           for (uint32_t done = 0; done < bytes; done += 32768u) {
             const uint32_t piece = min(32768u, bytes - done);
             bulk_load(a_ring + off + done, src + done, piece, full);
@@ -269,65 +350,83 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    uint32_t use = 0;        // pipeline uses consumed
-    uint32_t acc_use[2] = {0, 0};
-    int local = 0;
-    for (int it = it_begin; it < it_end; ++it, ++local) {
-      const Item item = p.items[p.cta_items[it]];
-      const SuperRow sr = p.srows[item.srow];
-      __syncwarp();
-      if (lane < sr.seg_count) s_col[lane] = p.segs[sr.seg_begin + lane].tmem_col;
-      if (lane == 0) s_col[sr.seg_count] = sr.n_cols;
-      __syncwarp();
+    if (kPair && rank != 0) {
+      // ===================== peer CTA: forward "stage full" to the leader =====================
       if (lane == 0) {
-        const int as = (p.acc_stages == 2) ? (local & 1) : 0;
-        mbar_wait(bar_acc_empty + 8 * as, acc_use[as] & 1, 3);
-        ++acc_use[as];
-        tc_fence_after();
-        const uint32_t acc_base = tmem_base + as * p.acc_stage_cols;
-        for (int c = 0; c < sr.chunk_count; ++c, ++use) {
-          const uint32_t s = use % P;
-          mbar_wait(bar_full + 8 * s, (use / P) & 1, 4);
-          tc_fence_after();
-          uint32_t mask = meta[s].mask;
-          const int ksteps = meta[s].ksteps;
-          uint32_t a_addr = a_ring + meta[s].a_off;
-          const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
-          while (mask) {
-            const int m0 = __ffs(mask) - 1;
-            const uint32_t inv = ~(mask >> m0);
-            const int len = inv ? (__ffs(inv) - 1) : (32 - m0);
-            const int mend = m0 + len;
-            int m = m0;
-            while (m < mend) {
-              const int mstart = m;
-              const int col0 = s_col[mstart];
-              ++m;
-              while (m < mend && s_col[m + 1] - col0 <= 256) ++m;
-              const int N = s_col[m] - col0;
-              const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(N >> 3) << 17);
-              const uint64_t adesc = smem_desc(a_addr);
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                // +32 bytes along K inside the 128-byte swizzle row
-                tc_mma<kTf32>(acc_base + col0, pdesc + 2 * k, adesc + 2 * k, idesc);
-              }
-              a_addr += static_cast<uint32_t>(N) * 128u;
-            }
-            const uint32_t run = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-            mask &= ~(run << m0);
+        uint32_t use = 0;
+        const uint32_t remote = map_to_cta(bar_peer_full, 0);
+        for (int it = it_begin; it < it_end; ++it) {
+          const SuperRow sr = p.srows[p.items[p.cta_items[it]].srow];
+          for (int c = 0; c < sr.chunk_count; ++c, ++use) {
+            const uint32_t s = use % P;
+            mbar_wait(bar_full + 8 * s, (use / P) & 1, 6);
+            mbar_arrive_remote(remote + 8 * s);
           }
-          tc_commit(bar_empty + 8 * s);
         }
-        tc_commit(bar_acc_full + 8 * as);
       }
+    } else {
+      // ===================== MMA issuer (leader CTA) =====================
+      uint32_t use = 0;        // pipeline uses consumed
+      uint32_t acc_use[2] = {0, 0};
+      int local = 0;
+      for (int it = it_begin; it < it_end; ++it, ++local) {
+        const Item item = p.items[p.cta_items[it]];
+        const SuperRow sr = p.srows[item.srow];
+        __syncwarp();
+        if (lane < sr.seg_count) s_col[lane] = p.segs[sr.seg_begin + lane].tmem_col;
+        if (lane == 0) s_col[sr.seg_count] = sr.n_cols;
+        __syncwarp();
+        if (lane == 0) {
+          const int as = (p.acc_stages == 2) ? (local & 1) : 0;
+          mbar_wait(bar_acc_empty + 8 * as, acc_use[as] & 1, 3);
+          ++acc_use[as];
+          tc_fence_after();
+          const uint32_t acc_base = tmem_base + as * p.acc_stage_cols;
+          for (int c = 0; c < sr.chunk_count; ++c, ++use) {
+            const uint32_t s = use % P;
+            mbar_wait(bar_full + 8 * s, (use / P) & 1, 4);
+            if constexpr (kPair) mbar_wait(bar_peer_full + 8 * s, (use / P) & 1, 7);
+            tc_fence_after();
+            uint32_t mask = meta[s].mask;
+            const int ksteps = meta[s].ksteps;
+            uint32_t a_addr = a_ring + meta[s].a_off;
+            const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
+            while (mask) {
+              const int m0 = __ffs(mask) - 1;
+              const uint32_t inv = ~(mask >> m0);
+              const int len = inv ? (__ffs(inv) - 1) : (32 - m0);
+              const int mend = m0 + len;
+              int m = m0;
+              while (m < mend) {   // same run decomposition as the host packer (for_each_run)
+                const int mstart = m;
+                const int col0 = s_col[mstart];
+                ++m;
+                while (m < mend && s_col[m + 1] - col0 <= 256) ++m;
+                const int N = s_col[m] - col0;
+                const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(N >> 3) << 17);
+                const uint64_t adesc = smem_desc(a_addr);
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  // +32 bytes along K inside the 128-byte swizzle row
+                  tc_mma<kTf32, kPair>(acc_base + col0, pdesc + 2 * k, adesc + 2 * k, idesc);
+                }
+                a_addr += static_cast<uint32_t>(N >> kShare) * 128u;
+              }
+              const uint32_t run = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
+              mask &= ~(run << m0);
+            }
+            tc_commit<kPair>(bar_empty + 8 * s);
+          }
+          tc_commit<kPair>(bar_acc_full + 8 * as);
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5, every CTA) =====================
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t acc_empty_remote = kPair ? map_to_cta(bar_acc_empty, 0) : 0u;
     // Zero every accumulator once; the MMAs always accumulate and the epilogue
     // re-zeroes what it drains.
     for (int c0 = 0; c0 < 512; c0 += 16) tmem_st16_zero(t_lane + c0);
@@ -335,8 +434,13 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(bar_acc_empty);
-      if (p.acc_stages == 2) mbar_arrive(bar_acc_empty + 8);
+      if (rank == 0) {
+        mbar_arrive(bar_acc_empty);
+        if (p.acc_stages == 2) mbar_arrive(bar_acc_empty + 8);
+      } else {
+        mbar_arrive_remote(acc_empty_remote);
+        if (p.acc_stages == 2) mbar_arrive_remote(acc_empty_remote + 8);
+      }
     }
     uint32_t acc_use[2] = {0, 0};
     int local = 0;
@@ -349,7 +453,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       ++acc_use[as];
       tc_fence_after();
       const uint32_t t_acc = t_lane + as * p.acc_stage_cols;
-      const int j = item.j0 + q * 32 + lane;
+      const int j = item.j0 + static_cast<int>(rank) * kTileJ + q * 32 + lane;
       const bool jv = j < p.n;
       float* cj = p.C + static_cast<int64_t>(j) * p.c_sj;
       for (int sidx = 0; sidx < sr.seg_count; ++sidx) {
@@ -391,17 +495,27 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar_acc_empty + 8 * as);
+        else mbar_arrive_remote(acc_empty_remote + 8 * as);
+      }
     }
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(512u)
-                 : "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(512u)
+                   : "memory");
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(512u)
+                   : "memory");
+    }
   }
 }
 
@@ -453,18 +567,29 @@ cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
     *err = "invalid pipeline configuration (shared memory)";
     return cudaErrorInvalidConfiguration;
   }
-  cudaError_t e;
-  if (p.kind_tf32) {
-    e = cudaFuncSetAttribute(spmm_vbr_sm100<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem);
-    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
-    spmm_vbr_sm100<true><<<grid, kSpmmThreads, smem, stream>>>(tmap, p);
-  } else {
-    e = cudaFuncSetAttribute(spmm_vbr_sm100<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem);
-    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
-    spmm_vbr_sm100<false><<<grid, kSpmmThreads, smem, stream>>>(tmap, p);
+  if (p.pair && (grid & 1)) {
+    *err = "pair mode needs an even grid";
+    return cudaErrorInvalidConfiguration;
   }
+  typedef void (*KernelFn)(const CUtensorMap, const SpmmParams);
+  KernelFn fn = p.kind_tf32 ? (p.pair ? spmm_vbr_sm100<true, true> : spmm_vbr_sm100<true, false>)
+                            : (p.pair ? spmm_vbr_sm100<false, true> : spmm_vbr_sm100<false, false>);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(kSpmmThreads, 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.pair ? 2 : 1;   // the two CTAs of a pair share one TPC
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, fn, tmap, p);
+  if (e != cudaSuccess) { *err = "spmm kernel launch"; return e; }
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "spmm kernel launch";
   return e;

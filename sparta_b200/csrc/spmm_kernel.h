@@ -25,6 +25,7 @@ struct SpmmParams {
   int32_t         a_ring_bytes; // bytes of the A-image ring (multiple of 1024)
   int32_t         acc_stages;   // 1 or 2 TMEM accumulator stages
   int32_t         acc_stage_cols; // 512 / acc_stages
+  int32_t         pair;         // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2); cta_ptr is per pair
 };
 
 constexpr int kSpmmThreads   = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue

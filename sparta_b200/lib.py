@@ -27,7 +27,8 @@ class Options(C.Structure):
         ("b_layout", C.c_int32), ("c_layout", C.c_int32), ("accumulate", C.c_int32),
         ("seg_rows", C.c_int32), ("acc_cols", C.c_int32), ("panel_stages", C.c_int32),
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
-        ("reserved", C.c_int32 * 8),
+        ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -39,6 +40,7 @@ class Stats(C.Structure):
         ("a_packed_bytes", C.c_int64), ("b_bytes", C.c_int64), ("c_bytes", C.c_int64),
         ("grid", C.c_int32), ("smem_bytes", C.c_int32), ("sched_imbalance", C.c_double),
         ("upload_ms", C.c_double), ("kernel_launches", C.c_int64),
+        ("team", C.c_int32), ("cta_pair", C.c_int32),
     ]
 
     def as_dict(self):

@@ -38,44 +38,73 @@ def read_image(store, off16, h_pad, esize):
     return out
 
 
+def runs_of(mask, cols):
+    """Python port of for_each_run (csrc/schedule.h): (m_begin, m_end, N) per MMA run."""
+    out = []
+    m = 0
+    count = len(cols) - 1
+    while m < count:
+        if not (mask >> m) & 1:
+            m += 1
+            continue
+        mend = m
+        while mend < count and (mask >> mend) & 1:
+            mend += 1
+        while m < mend:
+            mstart = m
+            col0 = cols[mstart]
+            m += 1
+            while m < mend and cols[m + 1] - col0 <= 256:
+                m += 1
+            out.append((mstart, m, cols[m] - col0))
+    return out
+
+
 def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
     """Bm: [n, ldb>=cols] (row j = column j of B).  Returns C as [n, rows]."""
     segs, srows, chunks, items = plan["segs"], plan["srows"], plan["chunks"], plan["items"]
     katom, kstep = 128 // esize, 32 // esize
+    nshare = 2 if plan["stats"]["cta_pair"] else 1
     store = pack_images(plan["jobs"], mab, int(plan["stats"]["a_packed_bytes"]), esize)
     Cm = np.full((n, rows), np.nan, dtype=np.float32)
     visited = np.zeros(len(items), dtype=bool)
-    for cta in range(len(plan["cta_ptr"]) - 1):
-        for it in plan["cta_items"][plan["cta_ptr"][cta]:plan["cta_ptr"][cta + 1]]:
+    assert len(plan["cta_ptr"]) - 1 == plan["stats"]["grid"] // nshare
+    for worker in range(len(plan["cta_ptr"]) - 1):
+        for it in plan["cta_items"][plan["cta_ptr"][worker]:plan["cta_ptr"][worker + 1]]:
             assert not visited[it]
             visited[it] = True
             item = items[it]
             sr = srows[item["srow"]]
-            j0 = int(item["j0"])
-            acc = np.zeros((128, int(sr["n_cols"])), dtype=np.float32)
-            for ch in chunks[sr["chunk_begin"]:sr["chunk_begin"] + sr["chunk_count"]]:
-                panel = np.zeros((128, katom), dtype=np.float32)  # TMA box, zero fill out of bounds
-                k0 = int(ch["k0"])
-                assert (k0 * esize) % 16 == 0, "TMA needs a 16-byte aligned k coordinate"
-                kk = max(0, min(katom, cols - k0))
+            sg_all = segs[sr["seg_begin"]:sr["seg_begin"] + sr["seg_count"]]
+            tcols = [int(c) for c in sg_all["tmem_col"]] + [int(sr["n_cols"])]
+            for cta in range(nshare):      # each CTA of a pair owns 128 of the item's columns
+                j0 = int(item["j0"]) + cta * 128
                 jj = max(0, min(128, n - j0))
-                panel[:jj, :kk] = Bm[j0:j0 + jj, k0:k0 + kk]
-                kuse = int(ch["ksteps"]) * kstep
-                off16 = int(ch["a_off16"])
-                used = 0
-                for m in range(int(sr["seg_count"])):
-                    if not (int(ch["mask"]) >> m) & 1:
-                        continue
-                    sg = segs[sr["seg_begin"] + m]
-                    img = read_image(store, off16, int(sg["h_pad"]), esize)
-                    acc[:, sg["tmem_col"]:sg["tmem_col"] + sg["h_pad"]] += panel[:, :kuse] @ img[:, :kuse].T
-                    off16 += int(sg["h_pad"]) * 8
-                    used += int(sg["h_pad"]) * 128
-                assert used == int(ch["a_bytes"])
-            for m in range(int(sr["seg_count"])):
-                sg = segs[sr["seg_begin"] + m]
-                jj = max(0, min(128, n - j0))
-                Cm[j0:j0 + jj, sg["c_row0"]:sg["c_row0"] + sg["h"]] = \
-                    acc[:jj, sg["tmem_col"]:sg["tmem_col"] + sg["h"]]
+                acc = np.zeros((128, int(sr["n_cols"])), dtype=np.float32)
+                for ch in chunks[sr["chunk_begin"]:sr["chunk_begin"] + sr["chunk_count"]]:
+                    panel = np.zeros((128, katom), dtype=np.float32)  # TMA box, zero fill out of bounds
+                    k0 = int(ch["k0"])
+                    assert (k0 * esize) % 16 == 0, "TMA needs a 16-byte aligned k coordinate"
+                    kk = max(0, min(katom, cols - k0))
+                    if jj:
+                        panel[:jj, :kk] = Bm[j0:j0 + jj, k0:k0 + kk]
+                    kuse = int(ch["ksteps"]) * kstep
+                    share16 = int(ch["a_bytes"]) // nshare // 16
+                    cursor = [int(ch["a_off16"]) + c * share16 for c in range(nshare)]
+                    used = 0
+                    for (mb, me, N) in runs_of(int(ch["mask"]), tcols):
+                        assert N % 16 == 0 and N <= 256
+                        half = N // nshare
+                        parts = []
+                        for c in range(nshare):   # the MMA reads N/nshare rows from each CTA's smem
+                            parts.append(read_image(store, cursor[c], half, esize))
+                            cursor[c] += half * 8
+                        img = np.concatenate(parts, axis=0)
+                        acc[:, tcols[mb]:tcols[mb] + N] += panel[:, :kuse] @ img[:, :kuse].T
+                        used += N * 128
+                    assert used == int(ch["a_bytes"])
+                for sg in sg_all:
+                    Cm[j0:j0 + jj, sg["c_row0"]:sg["c_row0"] + sg["h"]] = \
+                        acc[:jj, sg["tmem_col"]:sg["tmem_col"] + sg["h"]]
     assert visited.all()
     return Cm

@@ -13,17 +13,20 @@ CASES = [
     (5, 70, 16, [3, 17, 1, 64, 30], 0.6, 130, {}),               # ragged heights, ragged cols, n tail
     (4, 64, 3, [4, 3, 1, 1], 0.7, 2, {}),                        # the TEST config's w = 3
     (3, 300, 100, [64, 64, 20], 0.8, 16, {}),                    # w > 64: two K slabs per block
-    (7, 128, 64, [64] * 7, 0.4, 256, {"acc_cols": 512}),         # 8-wide super-rows
+    (7, 128, 64, [64] * 7, 0.4, 256, {"acc_cols": 256}),         # 4-wide super-rows, two stages
+    (11, 256, 64, [64, 16, 64, 48, 64, 64, 32, 64, 64, 80, 64], 0.5, 300, {"row_order": 1}),  # runs split unevenly
     (2, 64, 32, [200, 70], 1.0, 8, {"seg_rows": 64}),            # tall block-rows split into segments
     (40, 64, 8, [1] * 40, 0.3, 8, {"acc_cols": 512}),            # many height-1 block-rows
     (3, 64, 16, [5, 0, 9], 0.9, 8, {}),                          # an empty block-row
 ]
 
 
+@pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
 @pytest.mark.parametrize("precision,esize", [("bf16", 2), ("tf32", 4)])
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_plan_interpreter_matches_oracle(oracle, lib, case, precision, esize):
+def test_plan_interpreter_matches_oracle(oracle, lib, case, precision, esize, pair):
     block_rows, cols, w, heights, density, n, opts = CASES[case]
+    opts = dict(opts, cta_pair=pair)
     rng = np.random.default_rng(100 + case)
     v = random_vbr(rng, block_rows, cols, w, heights, density, values="int")
     Bm = rng.integers(-3, 4, size=(n, cols)).astype(np.float32)
@@ -42,7 +45,8 @@ def test_plan_invariants(lib):
     rng = np.random.default_rng(7)
     heights = rng.integers(1, 130, size=60)
     v = random_vbr(rng, 60, 1000, 64, heights, 0.3)
-    plan = sparta_b200.vbr_plan(v["rows"], 1000, 64, v["row_part"], v["nzcount"], v["jab"], 700)
+    plan = sparta_b200.vbr_plan(v["rows"], 1000, 64, v["row_part"], v["nzcount"], v["jab"], 700, cta_pair=1,
+                                acc_cols=256)
     segs, srows, chunks = plan["segs"], plan["srows"], plan["chunks"]
     assert np.all(segs["h_pad"] % 16 == 0) and np.all(segs["h"] <= segs["h_pad"]) and np.all(segs["h"] > 0)
     assert segs["h"].sum() == v["rows"]
@@ -72,7 +76,7 @@ def test_plan_shard_range(lib, oracle):
     for i in range(3):
         lo, hi = int(cuts[i]), int(cuts[i + 1])
         plan = sparta_b200.vbr_plan(v["rows"], 256, 32, v["row_part"], v["nzcount"], v["jab"], n,
-                                    block_row_begin=lo, block_row_end=hi)
+                                    block_row_begin=lo, block_row_end=hi, cta_pair=1 + i % 2)
         rows_i = int(v["row_part"][hi] - v["row_part"][lo])
         # the shard's source offsets are relative to its first block
         mab_lo = int(sum(v["nzcount"][b] * 32 * 32 for b in range(lo)))

@@ -51,21 +51,27 @@ CASES = [
     (5, 70, 16, [3, 17, 1, 64, 30], 0.6, 130, {}),
     (4, 64, 3, [4, 3, 1, 1], 0.7, 2, {}),
     (3, 300, 100, [64, 64, 20], 0.8, 16, {}),
-    (7, 128, 64, [64] * 7, 0.4, 256, {"acc_cols": 512}),
+    (7, 128, 64, [64] * 7, 0.4, 256, {"acc_cols": 256}),
     (2, 64, 32, [200, 70], 1.0, 8, {}),
     (40, 64, 8, [1] * 40, 0.3, 8, {"acc_cols": 512}),
     (3, 64, 16, [5, 7, 9], 0.0, 8, {}),                    # no nonzero block at all -> C = 0
-    (24, 1024, 64, [64] * 24, 0.5, 384, {}),               # several items per CTA, pipeline wraps
+    (24, 1024, 64, [64] * 24, 0.5, 384, {"acc_cols": 256}),  # several items per CTA, pipeline wraps
+    (40, 2048, 64, [64] * 37 + [63, 30, 7], 0.5, 700, {"num_ctas": 8}),   # many items per worker, 512-col super-rows
     (9, 640, 64, [64, 63, 30, 64, 1, 128, 7, 64, 33], 0.7, 200, {"acc_cols": 512, "panel_stages": 3}),
     (16, 512, 64, [64] * 16, 1.0, 128, {"panel_stages": 2}),
     (3, 2048, 128, [256, 100, 16], 0.9, 64, {"seg_rows": 256, "acc_cols": 512}),
 ]
 
 
+MODES = {"single": dict(cta_pair=1), "pair": dict(cta_pair=2), "pair_input_order": dict(cta_pair=2, row_order=1)}
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
 @pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_integer_operands_bit_exact(oracle, lib, case, precision):
+def test_integer_operands_bit_exact(oracle, lib, case, precision, mode):
     block_rows, cols, w, heights, density, n, opts = CASES[case]
+    opts = dict(opts, **MODES[mode])
     rng = np.random.default_rng(100 + case)
     v = random_vbr(rng, block_rows, cols, w, heights, density, values="int")
     Bm = rng.integers(-3, 4, size=(n, cols)).astype(np.float32)
@@ -74,10 +80,12 @@ def test_integer_operands_bit_exact(oracle, lib, case, precision):
     assert np.array_equal(Cg, Cref)
 
 
+@pytest.mark.parametrize("mode", ["single", "pair"])
 @pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("case", [1, 3, 8, 9, 11])
-def test_real_operands_within_tolerance(oracle, lib, case, precision):
+def test_real_operands_within_tolerance(oracle, lib, case, precision, mode):
     block_rows, cols, w, heights, density, n, opts = CASES[case]
+    opts = dict(opts, **MODES[mode])
     rng = np.random.default_rng(200 + case)
     v = random_vbr(rng, block_rows, cols, w, heights, density, values="uniform")
     Bm = rng.random((n, cols), dtype=np.float32)  # uniform(0,1) like cuda_multiply.cpp:36-44
