@@ -124,6 +124,14 @@ int sparta_run(sparta_handle* h, float* dt_ms);
 int sparta_run_async(sparta_handle* h);
 int sparta_synchronize(sparta_handle* h);
 
+/* Diagnostic: one multiply with the timeline of one worker (a CTA, or a CTA pair) recorded in SM
+ * clock cycles.  records receives uint64[4][2][capacity][2] = zone x pair rank x index x {t0, t1}:
+ * zone 0 producer per chunk {entered, TMA issued}; zone 1 MMA issuer per chunk, rank 0 {own stage
+ * seen full, peer stage seen full}, rank 1 {peer stage seen full, MMAs issued}; zone 2 epilogue
+ * per item {accumulator ready, drained}; zone 3 MMA issuer per item {waiting for the accumulator,
+ * got it}.  Entries beyond what the worker executed stay zero. */
+int sparta_run_traced(sparta_handle* h, int32_t worker, uint64_t* records, int64_t capacity);
+
 /* Copy the result (rows x n fp32) out.  on_device != 0: C is a device pointer. */
 int sparta_get_C(sparta_handle* h, float* C, int64_t ld, int on_device);
 

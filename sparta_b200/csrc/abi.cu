@@ -444,7 +444,8 @@ int sparta_get_C(sparta_handle* h, float* C, int64_t ld, int on_device) {
   return copy_c(h, C, ld, on_device, false);
 }
 
-static int launch(sparta_handle* h) {
+static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int trace_worker = 0,
+                  int trace_cap = 0) {
   if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");
   if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called before run");
   CU_TRY(cudaSetDevice(h->device));
@@ -464,6 +465,9 @@ static int launch(sparta_handle* h) {
   const uint32_t mma_m = h->st.pair ? 256u : 128u;
   p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((mma_m >> 4) << 24);
   p.pair = h->st.pair;
+  p.trace = trace;
+  p.trace_worker = trace_worker;
+  p.trace_cap = trace_cap;
   p.kind_tf32 = h->sopt.precision == PREC_TF32;
   p.panel_stages = h->panel_stages;
   p.a_ring_bytes = h->a_ring_bytes;
@@ -477,6 +481,26 @@ static int launch(sparta_handle* h) {
 }
 
 int sparta_run_async(sparta_handle* h) { return launch(h); }
+
+int sparta_run_traced(sparta_handle* h, int32_t worker, uint64_t* records, int64_t capacity) {
+  if (!h || !records || capacity <= 0 || capacity > (1 << 24))
+    return fail(SPARTA_ERR_INVALID, "NULL handle/records or invalid capacity");
+  if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called before run");
+  CU_TRY(cudaSetDevice(h->device));
+  const size_t bytes = static_cast<size_t>(capacity) * 4 * 2 * 2 * sizeof(uint64_t);
+  unsigned long long* d = nullptr;
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&d), bytes));
+  cudaError_t e = cudaMemsetAsync(d, 0, bytes, h->stream);
+  int rc = SPARTA_OK;
+  if (e == cudaSuccess) rc = launch(h, d, worker, static_cast<int>(capacity));
+  if (e == cudaSuccess && rc == SPARTA_OK)
+    e = cudaMemcpyAsync(records, d, bytes, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && rc == SPARTA_OK) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(e, "traced run");
+  return SPARTA_OK;
+}
 
 int sparta_synchronize(sparta_handle* h) {
   if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");

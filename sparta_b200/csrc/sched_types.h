@@ -27,7 +27,9 @@ struct SuperRow {
   int32_t chunk_begin;  // into chunks[]
   int32_t chunk_count;
   int32_t n_cols;       // sum of h_pad (<= tmem columns per accumulator stage)
-  int32_t pad_[3];
+  uint32_t break_mask;  // bit m set: an MMA run may not continue from member m-1 into member m
+                        // (members are cut into fixed groups of <= 256 accumulator columns)
+  int32_t pad_[2];
 };
 
 struct Chunk {

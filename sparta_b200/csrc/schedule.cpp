@@ -82,6 +82,16 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
       ++s1;
     }
     cols_of[s1 - s0] = cols;
+    // fixed cuts so that no MMA run spans more than 256 accumulator columns
+    uint32_t break_mask = 0;
+    for (size_t s = s0, run_cols = 0; s < s1; ++s) {
+      if (run_cols + st.segs[s].h_pad > 256) {
+        break_mask |= 1u << (s - s0);
+        run_cols = 0;
+      }
+      run_cols += st.segs[s].h_pad;
+    }
+    sr.break_mask = break_mask;
     sr.seg_count = static_cast<int32_t>(s1 - s0);
     sr.n_cols = cols;
     sr.chunk_begin = static_cast<int32_t>(st.chunks.size());
@@ -133,7 +143,7 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
         // Images are laid out run by run (the unit of one MMA); in pair mode the first half of a
         // run's rows goes to CTA 0's share and the second half to CTA 1's (cta_group::2 reads
         // N/2 rows of the N operand from each CTA).
-        for_each_run(mask, cols_of, [&](int mb, int me, int N) {
+        for_each_run(mask, break_mask, cols_of, [&](int mb, int me, int N) {
           const int half = N / nshare;
           for (int m = mb; m < me; ++m) {
             const size_t s = s0 + m;

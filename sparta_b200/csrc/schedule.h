@@ -45,27 +45,25 @@ struct Structure {           // independent of the number of B columns
   int pair = 0;
 };
 
-// Decomposition of a chunk's member mask into MMA runs: maximal groups of consecutive present
-// members whose accumulators are adjacent and span at most 256 columns.  The kernel issues one
-// MMA (per K step) per run; in pair mode the run's rows are split half/half between the CTAs.
+// Decomposition of a chunk's member mask into MMA runs.  A run is a maximal group of
+// consecutive PRESENT members that does not cross a break (SuperRow::break_mask cuts the members
+// into fixed groups of at most 256 accumulator columns, the widest N of one tcgen05.mma).  The
+// kernel issues one MMA per K step per run; in pair mode the run's rows are split half/half
+// between the two CTAs.  The rule is presence-local on purpose: the kernel's producer warp
+// derives the runs of a chunk with one ballot-style expression per lane (spmm_kernel.cu).
 // cols[m] = first accumulator column of member m, cols[count] = total.  fn(m_begin, m_end, N).
+inline uint32_t run_starts(uint32_t mask, uint32_t break_mask) {
+  return mask & (~(mask << 1) | break_mask);
+}
 template <class F>
-inline void for_each_run(uint32_t mask, const int32_t* cols, F fn) {
-  while (mask) {
-    const int m0 = __builtin_ctz(mask);
-    const uint32_t inv = ~(mask >> m0);
-    const int len = inv ? __builtin_ctz(inv) : (32 - m0);
-    const int mend = m0 + len;
-    int m = m0;
-    while (m < mend) {
-      const int mstart = m;
-      const int col0 = cols[mstart];
-      ++m;
-      while (m < mend && cols[m + 1] - col0 <= 256) ++m;
-      fn(mstart, m, cols[m] - col0);
-    }
-    const uint32_t run = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-    mask &= ~(run << m0);
+inline void for_each_run(uint32_t mask, uint32_t break_mask, const int32_t* cols, F fn) {
+  uint32_t starts = run_starts(mask, break_mask);
+  while (starts) {
+    const int m0 = __builtin_ctz(starts);
+    starts &= starts - 1;
+    int m1 = m0 + 1;
+    while (m1 < 32 && ((mask >> m1) & 1) && !((break_mask >> m1) & 1)) ++m1;
+    fn(m0, m1, cols[m1] - cols[m0]);
   }
 }
 

@@ -56,18 +56,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// acquire at cluster scope: the observed arrival may come from the peer CTA of a pair
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
+// Note on scopes: every wait below uses the default (CTA-scope) acquire even when the arrival
+// comes from the peer CTA.  What those cross-CTA barriers order is shared memory written by TMA
+// and TMEM written by tcgen05.st, both consumed by tcgen05.mma behind tcgen05 fences -- no
+// generic-proxy global data.  A cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1
+// invalidate behind the long scoreboard) after every successful wait, which showed up as the
+// top stall in the first ncu capture of the pair kernel.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -87,6 +81,20 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// One lane of a CONVERGED warp.  tcgen05.mma, TMA and bulk-copy instructions take their
+// operands in uniform registers; issued under `if (lane == 0)` ptxas wraps each of them in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~250 cycles per MMA in the first trace).
+// Under elect.sync it knows exactly one lane is active and moves the operands over directly.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -97,7 +105,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
+  while (!mbar_try_wait(bar, parity)) {
     if (((++spins) & 0x3FF) == 0 && global_timer_ns() - t0 > 5000000000ull) {
       printf("sparta spmm: mbarrier wait timed out (cta %d thread %d tag %d parity %u)\n",
              blockIdx.x, threadIdx.x, tag, parity);
@@ -106,7 +114,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int t
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
 
@@ -213,11 +221,32 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
 }
 
 
+__device__ __forceinline__ unsigned long long sm_clock() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_put(const SpmmParams& p, bool on, int zone, uint32_t rank,
+                                          uint32_t idx, unsigned long long t0,
+                                          unsigned long long t1) {
+  if (on && idx < static_cast<uint32_t>(p.trace_cap)) {
+    unsigned long long* r =
+        p.trace + ((static_cast<size_t>(zone) * 2 + rank) * p.trace_cap + idx) * 2;
+    r[0] = t0;
+    r[1] = t1;
+  }
+}
+
+// What the producer warp leaves for the MMA warp in each pipeline stage: the chunk's MMA runs,
+// fully decoded (instruction descriptor, accumulator column, position inside the stage's A
+// images), so that the issuing warp only loads, shuffles and fires.
 struct StageMeta {
-  uint32_t mask;
+  uint32_t nruns;
   int32_t  ksteps;
-  uint32_t a_off;   // byte offset of this chunk's images inside the A ring
+  uint32_t a_off;     // byte offset of this chunk's images inside the A ring
   uint32_t pad_;
+  uint2    run[32];   // .x = tcgen05 instruction descriptor (N filled in)
+                      // .y = accumulator column << 16 | (byte offset inside the chunk >> 4)
 };
 
 // ------------------------------------------------------------------ kernel
@@ -244,17 +273,15 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   const uint32_t a_ring = base + P * kPanelBytes;
   uint8_t* ctrl = smem + P * kPanelBytes + p.a_ring_bytes;
   const uint32_t ctrl_u = a_ring + p.a_ring_bytes;
-  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | peer_full[8] | meta[8] |
-  //              tmem_ptr | starts[8] | cols[33]
+  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | tmem_ptr | starts[8] | meta[8]
   const uint32_t bar_full = ctrl_u;
   const uint32_t bar_empty = ctrl_u + 64;
   const uint32_t bar_acc_full = ctrl_u + 128;
   const uint32_t bar_acc_empty = ctrl_u + 144;
-  const uint32_t bar_peer_full = ctrl_u + 160;
-  StageMeta* meta = reinterpret_cast<StageMeta*>(ctrl + 224);
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(ctrl + 352);
-  uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 384);
-  int32_t* s_col = reinterpret_cast<int32_t*>(ctrl + 416);  // 33 ints
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
+  uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 192);
+  StageMeta* meta = reinterpret_cast<StageMeta*>(ctrl + 256);
+  static_assert(256 + kMaxPanelStages * sizeof(StageMeta) <= kSmemCtrlBytes, "control block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,9 +291,9 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      // leader of a pair: own producer + the peer's "my half has landed" relay
+      mbar_init(bar_full + 8 * s, (kPair && rank == 0) ? 2 : 1);
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_peer_full + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
@@ -296,18 +323,51 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
 
   const int it_begin = p.cta_ptr[worker];
   const int it_end = p.cta_ptr[worker + 1];
+  const bool tr = p.trace != nullptr && worker == p.trace_worker;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread, every CTA) =====================
-    if (lane == 0) {
-      const uint32_t RB = static_cast<uint32_t>(p.a_ring_bytes);
-      uint32_t iss = 0, rel = 0, head = 0;
-      for (int it = it_begin; it < it_end; ++it) {
-        const Item item = p.items[p.cta_items[it]];
-        const SuperRow sr = p.srows[item.srow];
-        const int j0 = item.j0 + static_cast<int>(rank) * kTileJ;
-        for (int c = 0; c < sr.chunk_count; ++c) {
-          const Chunk ch = p.chunks[sr.chunk_begin + c];
+    // ===================== TMA producer (warp 0 of every CTA) =====================
+    // The chunk records are fetched 32 at a time by the whole warp (one coalesced request per
+    // batch, the next batch in flight while this one is issued) and handed to lane 0 by
+    // shuffle: a dependent global load per chunk in a single thread would cap the issue rate
+    // at one chunk per L2 round trip.
+    const uint32_t RB = static_cast<uint32_t>(p.a_ring_bytes);
+    uint32_t iss = 0, rel = 0, head = 0;
+    for (int it = it_begin; it < it_end; ++it) {
+      const Item item = p.items[p.cta_items[it]];
+      const SuperRow sr = p.srows[item.srow];
+      const int j0 = item.j0 + static_cast<int>(rank) * kTileJ;
+      // lane m keeps member m's accumulator column and padded height (n_cols / 0 past the end)
+      int my_col = sr.n_cols, my_rows = 0;
+      if (lane < sr.seg_count) {
+        const Segment sg = p.segs[sr.seg_begin + lane];
+        my_col = sg.tmem_col;
+        my_rows = sg.h_pad;
+      }
+      const int4* recs = reinterpret_cast<const int4*>(p.chunks + sr.chunk_begin);
+      int4 nxt = make_int4(0, 0, 0, 0);
+      int nxt_ks = 0;
+      if (lane < sr.chunk_count) {
+        nxt = __ldg(recs + 2 * lane);
+        nxt_ks = __ldg(reinterpret_cast<const int*>(recs + 2 * lane + 1));
+      }
+      for (int c0 = 0; c0 < sr.chunk_count; c0 += 32) {
+        const int4 cur = nxt;
+        const int cur_ks = nxt_ks;
+        if (c0 + 32 + lane < sr.chunk_count) {
+          nxt = __ldg(recs + 2 * (c0 + 32 + lane));
+          nxt_ks = __ldg(reinterpret_cast<const int*>(recs + 2 * (c0 + 32 + lane) + 1));
+        }
+        const int batch = min(32, sr.chunk_count - c0);
+        for (int i = 0; i < batch; ++i) {
+          const int ch_k0 = __shfl_sync(0xFFFFFFFFu, cur.x, i);
+          const uint32_t ch_mask = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.y, i));
+          const uint32_t ch_off16 = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.z, i));
+          const uint32_t ch_bytes = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.w, i));
+          const int ch_ksteps = __shfl_sync(0xFFFFFFFFu, cur_ks, i);
+          // Everything below is warp-uniform: all lanes track the pipeline state, one elected
+          // lane touches shared memory and issues the copies.
+          const unsigned long long tp0 = tr ? sm_clock() : 0ull;
           // stage slot: the use that last occupied it must have been released
           while (iss >= static_cast<uint32_t>(P) && rel + P <= iss) {
             mbar_wait(bar_empty + 8 * (rel % P), (rel / P) & 1, 1);
@@ -315,7 +375,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
           }
           // contiguous space in the A ring (FIFO release order).  The offsets depend only on
           // the sequence of sizes, so both CTAs of a pair place every chunk at the same offset.
-          const uint32_t bytes = ch.a_bytes >> kShare;
+          const uint32_t bytes = ch_bytes >> kShare;
           uint32_t off;
           for (;;) {
             if (rel == iss) { off = 0; break; }
@@ -331,21 +391,49 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             ++rel;
           }
           const uint32_t s = iss % P;
-          starts[s] = off;
-          head = off + bytes;
-          meta[s].mask = ch.mask;
-          meta[s].ksteps = ch.ksteps;
-          meta[s].a_off = off;
           const uint32_t full = bar_full + 8 * s;
-          mbar_arrive_expect_tx(full, kPanelBytes + bytes);
-          tma_load_2d(panels + s * kPanelBytes, &tmap_b, ch.k0, j0, full);
-          const uint8_t* src = p.a_packed + static_cast<size_t>(ch.a_off16) * 16 +
+          const uint8_t* src = p.a_packed + static_cast<size_t>(ch_off16) * 16 +
                                static_cast<size_t>(rank) * bytes;
-          for (uint32_t done = 0; done < bytes; done += 32768u) {
-            const uint32_t piece = min(32768u, bytes - done);
-            bulk_load(a_ring + off + done, src + done, piece, full);
+          // Decode the chunk's MMA runs, one per lane that starts a run (same rule as the host
+          // packer's for_each_run): a run begins at a present member whose predecessor is absent
+          // or that sits on a fixed break, and extends to the next absent member or run start.
+          const uint32_t run_starts = ch_mask & (~(ch_mask << 1) | sr.break_mask);
+          const uint32_t present = (ch_mask >> lane) & 1u;
+          int incl = present ? my_rows : 0;      // prefix sum of present rows = image position
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
           }
+          const int excl = incl - (present ? my_rows : 0);
+          const uint32_t stop = (~ch_mask | run_starts) & ~((2u << lane) - 1u);
+          const int e = stop ? (__ffs(stop) - 1) : 32;
+          const int end_col_sh = __shfl_sync(0xFFFFFFFFu, my_col, e & 31);
+          const int N = ((e >= 32) ? sr.n_cols : end_col_sh) - my_col;
+          __syncwarp();   // every lane has read starts[] before it is overwritten
+          if ((run_starts >> lane) & 1u) {
+            const int ridx = __popc(run_starts & ((1u << lane) - 1u));
+            meta[s].run[ridx] = make_uint2(
+                p.idesc_base | (static_cast<uint32_t>(N >> 3) << 17),
+                (static_cast<uint32_t>(my_col) << 16) | ((static_cast<uint32_t>(excl >> kShare) * 128u) >> 4));
+          }
+          __syncwarp();
+          if (elect_one()) {
+            starts[s] = off;
+            meta[s].nruns = __popc(run_starts);
+            meta[s].ksteps = ch_ksteps;
+            meta[s].a_off = off;
+            mbar_arrive_expect_tx(full, kPanelBytes + bytes);
+            tma_load_2d(panels + s * kPanelBytes, &tmap_b, ch_k0, j0, full);
+            for (uint32_t done = 0; done < bytes; done += 32768u) {
+              const uint32_t piece = min(32768u, bytes - done);
+              bulk_load(a_ring + off + done, src + done, piece, full);
+            }
+            if (tr) trace_put(p, true, 0, rank, iss, tp0, sm_clock());
+          }
+          head = off + bytes;
           ++iss;
+          __syncwarp();
         }
       }
     }
@@ -354,7 +442,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       // ===================== peer CTA: forward "stage full" to the leader =====================
       if (lane == 0) {
         uint32_t use = 0;
-        const uint32_t remote = map_to_cta(bar_peer_full, 0);
+        const uint32_t remote = map_to_cta(bar_full, 0);
         for (int it = it_begin; it < it_end; ++it) {
           const SuperRow sr = p.srows[p.items[p.cta_items[it]].srow];
           for (int c = 0; c < sr.chunk_count; ++c, ++use) {
@@ -365,60 +453,56 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
         }
       }
     } else {
-      // ===================== MMA issuer (leader CTA) =====================
+      // ===================== MMA issuer (leader CTA, converged warp) =====================
       uint32_t use = 0;        // pipeline uses consumed
       uint32_t acc_use[2] = {0, 0};
       int local = 0;
       for (int it = it_begin; it < it_end; ++it, ++local) {
         const Item item = p.items[p.cta_items[it]];
-        const SuperRow sr = p.srows[item.srow];
-        __syncwarp();
-        if (lane < sr.seg_count) s_col[lane] = p.segs[sr.seg_begin + lane].tmem_col;
-        if (lane == 0) s_col[sr.seg_count] = sr.n_cols;
-        __syncwarp();
-        if (lane == 0) {
-          const int as = (p.acc_stages == 2) ? (local & 1) : 0;
-          mbar_wait(bar_acc_empty + 8 * as, acc_use[as] & 1, 3);
-          ++acc_use[as];
+        const int chunk_count = p.srows[item.srow].chunk_count;
+        const int as = (p.acc_stages == 2) ? (local & 1) : 0;
+        const unsigned long long ta0 = tr ? sm_clock() : 0ull;
+        mbar_wait(bar_acc_empty + 8 * as, acc_use[as] & 1, 3);
+        if (tr && lane == 0) trace_put(p, true, 3, 0, static_cast<uint32_t>(local), ta0, sm_clock());
+        ++acc_use[as];
+        tc_fence_after();
+        const uint32_t acc_base = tmem_base + as * p.acc_stage_cols;
+        for (int c = 0; c < chunk_count; ++c, ++use) {
+          const uint32_t s = use % P;
+          mbar_wait(bar_full + 8 * s, (use / P) & 1, 4);   // pair: own half AND the peer's relay
+          const unsigned long long tm0 = tr ? sm_clock() : 0ull;
           tc_fence_after();
-          const uint32_t acc_base = tmem_base + as * p.acc_stage_cols;
-          for (int c = 0; c < sr.chunk_count; ++c, ++use) {
-            const uint32_t s = use % P;
-            mbar_wait(bar_full + 8 * s, (use / P) & 1, 4);
-            if constexpr (kPair) mbar_wait(bar_peer_full + 8 * s, (use / P) & 1, 7);
-            tc_fence_after();
-            uint32_t mask = meta[s].mask;
-            const int ksteps = meta[s].ksteps;
-            uint32_t a_addr = a_ring + meta[s].a_off;
-            const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
-            while (mask) {
-              const int m0 = __ffs(mask) - 1;
-              const uint32_t inv = ~(mask >> m0);
-              const int len = inv ? (__ffs(inv) - 1) : (32 - m0);
-              const int mend = m0 + len;
-              int m = m0;
-              while (m < mend) {   // same run decomposition as the host packer (for_each_run)
-                const int mstart = m;
-                const int col0 = s_col[mstart];
-                ++m;
-                while (m < mend && s_col[m + 1] - col0 <= 256) ++m;
-                const int N = s_col[m] - col0;
-                const uint32_t idesc = p.idesc_base | (static_cast<uint32_t>(N >> 3) << 17);
-                const uint64_t adesc = smem_desc(a_addr);
+          const StageMeta* mt = meta + s;
+          const uint4 hdr = *reinterpret_cast<const uint4*>(mt);   // nruns, ksteps, a_off
+          const int nruns = static_cast<int>(hdr.x);
+          const int ksteps = static_cast<int>(hdr.y);
+          uint2 rec = make_uint2(0u, 0u);
+          if (lane < nruns) rec = mt->run[lane];
+          const uint32_t a_base = a_ring + hdr.z;
+          const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
+          for (int r = 0; r < nruns; ++r) {
+            const uint32_t idesc = __shfl_sync(0xFFFFFFFFu, rec.x, r);
+            const uint32_t where = __shfl_sync(0xFFFFFFFFu, rec.y, r);
+            const uint64_t adesc = smem_desc(a_base + ((where & 0xFFFFu) << 4));
+            const uint32_t d_tmem = acc_base + (where >> 16);
+            if (elect_one()) {
 #pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                  // +32 bytes along K inside the 128-byte swizzle row
-                  tc_mma<kTf32, kPair>(acc_base + col0, pdesc + 2 * k, adesc + 2 * k, idesc);
-                }
-                a_addr += static_cast<uint32_t>(N >> kShare) * 128u;
+              for (int k = 0; k < ksteps; ++k) {
+                // +32 bytes along K inside the 128-byte swizzle row
+                tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
               }
-              const uint32_t run = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-              mask &= ~(run << m0);
             }
-            tc_commit<kPair>(bar_empty + 8 * s);
+            __syncwarp();
           }
-          tc_commit<kPair>(bar_acc_full + 8 * as);
+          if (elect_one()) tc_commit<kPair>(bar_empty + 8 * s);
+          __syncwarp();
+          if (tr && lane == 0) {   // rank-0 slot: stage seen full; rank-1 slot: {seen full, MMAs issued}
+            trace_put(p, true, 1, 0, use, tm0, tm0);
+            trace_put(p, true, 1, 1, use, tm0, sm_clock());
+          }
         }
+        if (elect_one()) tc_commit<kPair>(bar_acc_full + 8 * as);
+        __syncwarp();
       }
       __syncwarp();
     }
@@ -450,6 +534,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       const SuperRow sr = p.srows[item.srow];
       const int as = (p.acc_stages == 2) ? (local & 1) : 0;
       mbar_wait(bar_acc_full + 8 * as, acc_use[as] & 1, 5);
+      const unsigned long long te0 = (tr && warp == 2 && lane == 0) ? sm_clock() : 0ull;
       ++acc_use[as];
       tc_fence_after();
       const uint32_t t_acc = t_lane + as * p.acc_stage_cols;
@@ -498,6 +583,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       if (lane == 0) {
         if (rank == 0) mbar_arrive(bar_acc_empty + 8 * as);
         else mbar_arrive_remote(acc_empty_remote + 8 * as);
+        if (tr && warp == 2) trace_put(p, true, 2, rank, static_cast<uint32_t>(local), te0, sm_clock());
       }
     }
   }

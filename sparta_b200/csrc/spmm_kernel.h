@@ -26,11 +26,17 @@ struct SpmmParams {
   int32_t         acc_stages;   // 1 or 2 TMEM accumulator stages
   int32_t         acc_stage_cols; // 512 / acc_stages
   int32_t         pair;         // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2); cta_ptr is per pair
+  // optional timeline of one worker (sparta_run_traced): 4 zones x 2 ranks x trace_cap records of
+  // {t0, t1} SM clocks; zone 0 producer per chunk, 1 MMA per chunk, 2 epilogue per item,
+  // 3 MMA accumulator wait per item
+  unsigned long long* trace;
+  int32_t         trace_worker;
+  int32_t         trace_cap;
 };
 
 constexpr int kSpmmThreads   = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int kMaxPanelStages = 8;
-constexpr int kSmemCtrlBytes = 1024;  // barriers + metadata block at the end
+constexpr int kSmemCtrlBytes = 3072;  // barriers + per-stage run tables at the end
 constexpr int kSmemMax       = 232448; // 227 KB opt-in limit per CTA
 
 // Bytes of dynamic shared memory for a configuration (includes 1 KB slack used

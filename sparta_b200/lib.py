@@ -64,6 +64,7 @@ SIGNATURES = {
     "sparta_set_C": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
     "sparta_run": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "sparta_run_async": (C.c_int, [_vp]),
+    "sparta_run_traced": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
     "sparta_synchronize": (C.c_int, [_vp]),
     "sparta_get_C": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
     "sparta_C_device_ptr": (_vp, [_vp]),
@@ -206,6 +207,12 @@ class Handle:
         _check(load().sparta_run(self._h, C.byref(dt)))
         return dt.value
 
+    def run_traced(self, worker=0, capacity=16384):
+        """One multiply with worker's timeline: uint64[zone 4][rank 2][capacity][2] SM clocks."""
+        rec = np.zeros((4, 2, capacity, 2), dtype=np.uint64)
+        _check(load().sparta_run_traced(self._h, worker, _ptr(rec), capacity))
+        return rec
+
     def run_async(self):
         _check(load().sparta_run_async(self._h))
 
@@ -251,7 +258,7 @@ class Handle:
 
 SEG_DT = np.dtype([("c_row0", "<i4"), ("h", "<i4"), ("h_pad", "<i4"), ("tmem_col", "<i4")])
 SROW_DT = np.dtype([("seg_begin", "<i4"), ("seg_count", "<i4"), ("chunk_begin", "<i4"),
-                    ("chunk_count", "<i4"), ("n_cols", "<i4"), ("pad", "<i4", (3,))])
+                    ("chunk_count", "<i4"), ("n_cols", "<i4"), ("break_mask", "<u4"), ("pad", "<i4", (2,))])
 CHUNK_DT = np.dtype([("k0", "<i4"), ("mask", "<u4"), ("a_off16", "<u4"), ("a_bytes", "<u4"),
                      ("ksteps", "<i4"), ("pad", "<i4", (3,))])
 ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4")])

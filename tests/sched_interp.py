@@ -38,25 +38,18 @@ def read_image(store, off16, h_pad, esize):
     return out
 
 
-def runs_of(mask, cols):
+def runs_of(mask, break_mask, cols):
     """Python port of for_each_run (csrc/schedule.h): (m_begin, m_end, N) per MMA run."""
     out = []
-    m = 0
     count = len(cols) - 1
-    while m < count:
-        if not (mask >> m) & 1:
-            m += 1
+    starts = mask & (~(mask << 1) | break_mask) & 0xFFFFFFFF
+    for m0 in range(count):
+        if not (starts >> m0) & 1:
             continue
-        mend = m
-        while mend < count and (mask >> mend) & 1:
-            mend += 1
-        while m < mend:
-            mstart = m
-            col0 = cols[mstart]
-            m += 1
-            while m < mend and cols[m + 1] - col0 <= 256:
-                m += 1
-            out.append((mstart, m, cols[m] - col0))
+        m1 = m0 + 1
+        while m1 < count and (mask >> m1) & 1 and not (break_mask >> m1) & 1:
+            m1 += 1
+        out.append((m0, m1, cols[m1] - cols[m0]))
     return out
 
 
@@ -92,7 +85,7 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
                     share16 = int(ch["a_bytes"]) // nshare // 16
                     cursor = [int(ch["a_off16"]) + c * share16 for c in range(nshare)]
                     used = 0
-                    for (mb, me, N) in runs_of(int(ch["mask"]), tcols):
+                    for (mb, me, N) in runs_of(int(ch["mask"]), int(sr["break_mask"]), tcols):
                         assert N % 16 == 0 and N <= 256
                         half = N // nshare
                         parts = []
