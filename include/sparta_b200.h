@@ -221,7 +221,7 @@ int sparta_host_bellpack_free(sparta_host_bell* b);
 /* Host-only access to the schedule itself so the CPU test-suite can interpret it
  * (tests/sched_interp.py) without a GPU.  No arithmetic on matrix values happens
  * in the library on this path.  `which`: 0 segments, 1 super-rows, 2 chunks,
- * 3 items, 4 cta_ptr, 5 cta_items, 6 pack jobs (record layouts: csrc/sched_types.h).
+ * 3 items, 4 cta_ptr, 5 cta_items, 6 pack jobs, 7 run tables (record layouts: csrc/sched_types.h).
  * *data points into the plan and stays valid until sparta_plan_destroy. */
 typedef struct sparta_plan sparta_plan;
 int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_t block_rows,

@@ -84,6 +84,14 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _slack(Bm, w):
+    """VBR::multiply walks k < w in the last column block even when cols % w != 0 (vbr.cpp:362),
+    reading up to w-1 floats past the end of B's last column (the matching A entries are zero).
+    Append w finite zeros so that 0 * whatever-follows-the-buffer cannot turn into NaN."""
+    flat = _f(Bm).reshape(-1)
+    return np.concatenate([flat, np.zeros(w, dtype=np.float32)])
+
+
 class Oracle:
     def __init__(self):
         if not os.path.exists(ORACLE_SO):
@@ -135,7 +143,7 @@ class Oracle:
         """VBR::multiply restatement; returns C as [n, rows] (row j = column j of C)."""
         rows, cols = int(v["rows"]), int(v["cols"])
         ldb = cols if ldb is None else ldb
-        Bm = _f(Bm).reshape(-1)
+        Bm = _slack(Bm, int(v["block_col_size"]))
         Cm = np.zeros(n * rows, dtype=np.float32) if C_init is None else _f(C_init).reshape(-1).copy()
         rp, nz, jab, mab = _l(v["row_part"]), _l(v["nzcount"]), _l(v["jab"]), _f(v["mab"])
         self.lib.oracle_vbr_multiply(len(nz), int(v["block_col_size"]), _p(rp), _p(nz), _p(jab), _p(mab),
@@ -235,7 +243,7 @@ class Reference:
 
     def vbr_multiply(self, v, Bm, n):
         rows, cols = int(v["rows"]), int(v["cols"])
-        Bm = _f(Bm).reshape(-1)
+        Bm = _slack(Bm, int(v["block_col_size"]))
         Cm = np.zeros(n * rows, dtype=np.float32)
         rp, nz, jab, mab = _l(v["row_part"]), _l(v["nzcount"]), _l(v["jab"]), _f(v["mab"])
         self.lib.ref_vbr_multiply(rows, cols, len(nz), int(v["block_col_size"]), _p(rp), _p(nz), _p(jab),

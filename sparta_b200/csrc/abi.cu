@@ -62,6 +62,7 @@ struct sparta_handle {
   Segment* d_segs = nullptr;
   SuperRow* d_srows = nullptr;
   Chunk* d_chunks = nullptr;
+  uint32_t* d_tables = nullptr;
   uint8_t* d_a = nullptr;
   Item* d_items = nullptr;
   int32_t* d_cta_ptr = nullptr;
@@ -169,7 +170,7 @@ static const char* blockrows_from_bell(int64_t bs, int64_t ind_rows, int64_t ind
 static void free_handle(sparta_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->d_segs); cudaFree(h->d_srows); cudaFree(h->d_chunks); cudaFree(h->d_a);
+  cudaFree(h->d_segs); cudaFree(h->d_srows); cudaFree(h->d_chunks); cudaFree(h->d_tables); cudaFree(h->d_a);
   cudaFree(h->d_items); cudaFree(h->d_cta_ptr); cudaFree(h->d_cta_items);
   cudaFree(h->d_B); cudaFree(h->d_C);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -251,6 +252,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   H_TRY(upload_vec(h->st.segs, &h->d_segs, h->stream));
   H_TRY(upload_vec(h->st.srows, &h->d_srows, h->stream));
   H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
+  H_TRY(upload_vec(h->st.tables, &h->d_tables, h->stream));
   H_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_a), std::max<uint64_t>(h->st.a_bytes, 16)));
 
   if (!h->st.jobs.empty()) {
@@ -454,16 +456,12 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   memset(&p, 0, sizeof(p));
   p.items = h->d_items; p.cta_ptr = h->d_cta_ptr; p.cta_items = h->d_cta_items;
   p.srows = h->d_srows; p.segs = h->d_segs; p.chunks = h->d_chunks; p.a_packed = h->d_a;
+  p.tables = reinterpret_cast<const uint8_t*>(h->d_tables);
   p.C = h->d_C;
   p.c_sr = h->c_row_major ? h->ldc : 1;
   p.c_sj = h->c_row_major ? 1 : h->ldc;
   p.n = static_cast<int32_t>(h->n);
   p.accumulate = h->accumulate;
-  // tcgen05 instruction descriptor (kind::f16 / kind::tf32): D fp32 at [4,6), A/B
-  // format at [7,10)/[10,13) (0 f16, 1 bf16, 2 tf32), both K-major, M=128 at [24,29)
-  const uint32_t fmt = h->sopt.precision == PREC_BF16 ? 1u : (h->sopt.precision == PREC_FP16 ? 0u : 2u);
-  const uint32_t mma_m = h->st.pair ? 256u : 128u;
-  p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((mma_m >> 4) << 24);
   p.pair = h->st.pair;
   p.trace = trace;
   p.trace_worker = trace_worker;
@@ -756,6 +754,7 @@ int sparta_plan_array(sparta_plan* plan, int32_t which, const void** data, int64
     case 4: PLAN_ARR(plan->as.cta_ptr, int32_t);
     case 5: PLAN_ARR(plan->as.cta_items, int32_t);
     case 6: PLAN_ARR(plan->st.jobs, PackJob);
+    case 7: PLAN_ARR(plan->st.tables, uint32_t);
   }
 #undef PLAN_ARR
   return fail(SPARTA_ERR_INVALID, "unknown plan array id");

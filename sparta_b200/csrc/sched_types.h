@@ -38,8 +38,18 @@ struct Chunk {
   uint32_t a_off16;   // offset of the packed A images of this chunk, 16-byte units
   uint32_t a_bytes;   // total bytes of those images (sum h_pad*128 over set bits)
   int32_t  ksteps;    // MMA K steps to issue (1..4), covers the block's true width
-  int32_t  pad_[3];
+  uint32_t tbl_bytes; // bytes of this chunk's run table (16 + 8 per run, rounded up to 16)
+  uint32_t tbl_off16; // its offset in the table stream, 16-byte units
+  int32_t  pad_;
 };
+
+// Run table of a chunk: what the MMA-issuing warp executes, decoded on the host and streamed
+// into shared memory by the copy engine next to the A images.  Tables are stored back to back:
+//   word 0 nruns, word 1 ksteps, words 2-3 zero, then per run
+//   .x = tcgen05 instruction descriptor (M, N, formats)
+//   .y = accumulator column << 16 | (byte offset of the run's rows inside the CTA's images >> 4)
+constexpr int kTableWords = 4 + 2 * 32;
+constexpr int kTableBytes = kTableWords * 4;   // 272: the largest table (32 runs)
 
 struct Item {
   int32_t srow;       // super-row id

@@ -27,6 +27,10 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
   const int kstep = 32 / esize;     // k elements per MMA (K = 16 for 16-bit, 8 for tf32)
   const int kalign = 16 / esize;    // TMA needs a 16-byte aligned start along k
   const int nshare = st.pair ? 2 : 1;
+  // tcgen05 instruction descriptor (kind::f16 / kind::tf32): D fp32 at [4,6), A/B format at
+  // [7,10)/[10,13) (0 f16, 1 bf16, 2 tf32), both operands K-major, N>>3 at [17,23), M>>4 at [24,29)
+  const uint32_t fmt = opt.precision == PREC_BF16 ? 1u : (opt.precision == PREC_FP16 ? 0u : 2u);
+  const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | (((st.pair ? 256u : 128u) >> 4) << 24);
 
   // 0. order of the block-rows.  C rows are written wherever row_part says, so the order in
   //    which block-rows are grouped into super-rows is free: putting block-rows with similar
@@ -140,11 +144,18 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
         const uint32_t share = bytes / nshare;       // bytes each CTA stages for this chunk
         uint32_t cursor[2] = {0, 0};                 // write position inside each CTA's share
         const uint64_t chunk_base = st.a_bytes;
+        const size_t tbl = st.tables.size();
+        st.tables.resize(tbl + kTableWords, 0u);
+        uint32_t nruns = 0, rows_before = 0;   // rows_before: per-CTA rows of the earlier runs
         // Images are laid out run by run (the unit of one MMA); in pair mode the first half of a
         // run's rows goes to CTA 0's share and the second half to CTA 1's (cta_group::2 reads
         // N/2 rows of the N operand from each CTA).
         for_each_run(mask, break_mask, cols_of, [&](int mb, int me, int N) {
           const int half = N / nshare;
+          st.tables[tbl + 4 + 2 * nruns] = idesc_base | (static_cast<uint32_t>(N >> 3) << 17);
+          st.tables[tbl + 5 + 2 * nruns] = (static_cast<uint32_t>(cols_of[mb]) << 16) | ((rows_before * 128u) >> 4);
+          ++nruns;
+          rows_before += static_cast<uint32_t>(half);
           for (int m = mb; m < me; ++m) {
             const size_t s = s0 + m;
             const int64_t b = seg_src[s].b;
@@ -169,6 +180,12 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
             }
           }
         });
+        st.tables[tbl] = nruns;
+        st.tables[tbl + 1] = static_cast<uint32_t>(ch.ksteps);
+        ch.tbl_bytes = 16u + 8u * ((nruns + 1u) & ~1u);   // multiple of 16 for the bulk copy
+        if ((tbl >> 2) > UINT32_MAX) return "run tables exceed 64 GiB";
+        ch.tbl_off16 = static_cast<uint32_t>(tbl >> 2);
+        st.tables.resize(tbl + ch.tbl_bytes / 4);
         ch.a_bytes = bytes;
         st.a_bytes += bytes;
         st.max_chunk_bytes = std::max(st.max_chunk_bytes, share);

@@ -36,6 +36,7 @@ struct Structure {           // independent of the number of B columns
   std::vector<SuperRow> srows;
   std::vector<Chunk>    chunks;
   std::vector<PackJob>  jobs;
+  std::vector<uint32_t> tables;      // run tables of all chunks, back to back (see sched_types.h)
   std::vector<double>   srow_cost;   // modelled tensor cycles per column tile
   uint64_t a_bytes = 0;              // bytes of packed A images
   int64_t  nztot = 0;                // sum over blocks of h*w (the reference's VBR::nztot)

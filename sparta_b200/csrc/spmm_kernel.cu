@@ -135,6 +135,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       : "memory");
 }
 
+// Pull a byte range into L2 ahead of the copy that will need it (no shared memory involved).
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -237,17 +241,6 @@ __device__ __forceinline__ void trace_put(const SpmmParams& p, bool on, int zone
   }
 }
 
-// What the producer warp leaves for the MMA warp in each pipeline stage: the chunk's MMA runs,
-// fully decoded (instruction descriptor, accumulator column, position inside the stage's A
-// images), so that the issuing warp only loads, shuffles and fires.
-struct StageMeta {
-  uint32_t nruns;
-  int32_t  ksteps;
-  uint32_t a_off;     // byte offset of this chunk's images inside the A ring
-  uint32_t pad_;
-  uint2    run[32];   // .x = tcgen05 instruction descriptor (N filled in)
-                      // .y = accumulator column << 16 | (byte offset inside the chunk >> 4)
-};
 
 // ------------------------------------------------------------------ kernel
 // kPair = false: one CTA owns a (super-row, 128-column tile) item; MMAs are cta_group::1, M = 128.
@@ -273,15 +266,17 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   const uint32_t a_ring = base + P * kPanelBytes;
   uint8_t* ctrl = smem + P * kPanelBytes + p.a_ring_bytes;
   const uint32_t ctrl_u = a_ring + p.a_ring_bytes;
-  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | tmem_ptr | starts[8] | meta[8]
+  // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | tmem_ptr | starts[8] |
+  //              run tables[8] (kTableBytes each, filled by the copy engine)
   const uint32_t bar_full = ctrl_u;
   const uint32_t bar_empty = ctrl_u + 64;
   const uint32_t bar_acc_full = ctrl_u + 128;
   const uint32_t bar_acc_empty = ctrl_u + 144;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
   uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 192);
-  StageMeta* meta = reinterpret_cast<StageMeta*>(ctrl + 256);
-  static_assert(256 + kMaxPanelStages * sizeof(StageMeta) <= kSmemCtrlBytes, "control block too small");
+  const uint32_t tables_u = ctrl_u + 256;
+  const uint8_t* tables_s = ctrl + 256;
+  static_assert(256 + kMaxPanelStages * kTableBytes <= kSmemCtrlBytes, "control block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -326,60 +321,57 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   const bool tr = p.trace != nullptr && worker == p.trace_worker;
 
   if (warp == 0) {
-    // ===================== TMA producer (warp 0 of every CTA) =====================
-    // The chunk records are fetched 32 at a time by the whole warp (one coalesced request per
-    // batch, the next batch in flight while this one is issued) and handed to lane 0 by
-    // shuffle: a dependent global load per chunk in a single thread would cap the issue rate
-    // at one chunk per L2 round trip.
+    // ===================== TMA producer (warp 0 of every CTA, converged) =====================
+    // Chunk records are fetched 32 at a time by the whole warp (one coalesced request per
+    // batch, the next batch in flight while this one is issued) and broadcast by shuffle: a
+    // dependent global load per chunk would cap the issue rate at one chunk per L2 round trip.
+    // Per chunk the warp only waits for a stage, places the images in the ring and fires three
+    // copies (B panel, A images, run table); everything the MMA warp needs was decoded on the host.
     const uint32_t RB = static_cast<uint32_t>(p.a_ring_bytes);
-    uint32_t iss = 0, rel = 0, head = 0;
+    uint32_t iss = 0, rel = 0, head = 0;           // uses issued / uses known released / ring head
+    uint32_t iss_slot = 0, rel_slot = 0, rel_phase = 0;
+    auto release_one = [&](int tag) {              // observe the release of the oldest use
+      mbar_wait(bar_empty + 8 * rel_slot, rel_phase, tag);
+      ++rel;
+      if (++rel_slot == static_cast<uint32_t>(P)) { rel_slot = 0; rel_phase ^= 1u; }
+    };
     for (int it = it_begin; it < it_end; ++it) {
       const Item item = p.items[p.cta_items[it]];
       const SuperRow sr = p.srows[item.srow];
       const int j0 = item.j0 + static_cast<int>(rank) * kTileJ;
-      // lane m keeps member m's accumulator column and padded height (n_cols / 0 past the end)
-      int my_col = sr.n_cols, my_rows = 0;
-      if (lane < sr.seg_count) {
-        const Segment sg = p.segs[sr.seg_begin + lane];
-        my_col = sg.tmem_col;
-        my_rows = sg.h_pad;
-      }
       const int4* recs = reinterpret_cast<const int4*>(p.chunks + sr.chunk_begin);
       int4 nxt = make_int4(0, 0, 0, 0);
-      int nxt_ks = 0;
+      int2 nxt_t = make_int2(0, 0);
       if (lane < sr.chunk_count) {
         nxt = __ldg(recs + 2 * lane);
-        nxt_ks = __ldg(reinterpret_cast<const int*>(recs + 2 * lane + 1));
+        const int4 hi = __ldg(recs + 2 * lane + 1);
+        nxt_t = make_int2(hi.y, hi.z);             // tbl_bytes, tbl_off16
       }
       for (int c0 = 0; c0 < sr.chunk_count; c0 += 32) {
         const int4 cur = nxt;
-        const int cur_ks = nxt_ks;
+        const int2 cur_t = nxt_t;
         if (c0 + 32 + lane < sr.chunk_count) {
           nxt = __ldg(recs + 2 * (c0 + 32 + lane));
-          nxt_ks = __ldg(reinterpret_cast<const int*>(recs + 2 * (c0 + 32 + lane) + 1));
+          const int4 hi = __ldg(recs + 2 * (c0 + 32 + lane) + 1);
+          nxt_t = make_int2(hi.y, hi.z);
         }
         const int batch = min(32, sr.chunk_count - c0);
         for (int i = 0; i < batch; ++i) {
           const int ch_k0 = __shfl_sync(0xFFFFFFFFu, cur.x, i);
-          const uint32_t ch_mask = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.y, i));
           const uint32_t ch_off16 = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.z, i));
           const uint32_t ch_bytes = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.w, i));
-          const int ch_ksteps = __shfl_sync(0xFFFFFFFFu, cur_ks, i);
-          // Everything below is warp-uniform: all lanes track the pipeline state, one elected
-          // lane touches shared memory and issues the copies.
+          const uint32_t tb_bytes = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur_t.x, i));
+          const uint32_t tb_off16 = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur_t.y, i));
           const unsigned long long tp0 = tr ? sm_clock() : 0ull;
           // stage slot: the use that last occupied it must have been released
-          while (iss >= static_cast<uint32_t>(P) && rel + P <= iss) {
-            mbar_wait(bar_empty + 8 * (rel % P), (rel / P) & 1, 1);
-            ++rel;
-          }
+          while (iss - rel >= static_cast<uint32_t>(P)) release_one(1);
           // contiguous space in the A ring (FIFO release order).  The offsets depend only on
           // the sequence of sizes, so both CTAs of a pair place every chunk at the same offset.
           const uint32_t bytes = ch_bytes >> kShare;
           uint32_t off;
           for (;;) {
             if (rel == iss) { off = 0; break; }
-            const uint32_t tail = starts[rel % P];
+            const uint32_t tail = starts[rel_slot];
             if (head > tail) {
               if (head + bytes <= RB) { off = head; break; }
               if (bytes <= tail) { off = 0; break; }
@@ -387,74 +379,49 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
               off = head;
               break;
             }
-            mbar_wait(bar_empty + 8 * (rel % P), (rel / P) & 1, 2);
-            ++rel;
+            release_one(2);
           }
-          const uint32_t s = iss % P;
+          const uint32_t s = iss_slot;
           const uint32_t full = bar_full + 8 * s;
           const uint8_t* src = p.a_packed + static_cast<size_t>(ch_off16) * 16 +
                                static_cast<size_t>(rank) * bytes;
-          // Decode the chunk's MMA runs, one per lane that starts a run (same rule as the host
-          // packer's for_each_run): a run begins at a present member whose predecessor is absent
-          // or that sits on a fixed break, and extends to the next absent member or run start.
-          const uint32_t run_starts = ch_mask & (~(ch_mask << 1) | sr.break_mask);
-          const uint32_t present = (ch_mask >> lane) & 1u;
-          int incl = present ? my_rows : 0;      // prefix sum of present rows = image position
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += t;
-          }
-          const int excl = incl - (present ? my_rows : 0);
-          const uint32_t stop = (~ch_mask | run_starts) & ~((2u << lane) - 1u);
-          const int e = stop ? (__ffs(stop) - 1) : 32;
-          const int end_col_sh = __shfl_sync(0xFFFFFFFFu, my_col, e & 31);
-          const int N = ((e >= 32) ? sr.n_cols : end_col_sh) - my_col;
           __syncwarp();   // every lane has read starts[] before it is overwritten
-          if ((run_starts >> lane) & 1u) {
-            const int ridx = __popc(run_starts & ((1u << lane) - 1u));
-            meta[s].run[ridx] = make_uint2(
-                p.idesc_base | (static_cast<uint32_t>(N >> 3) << 17),
-                (static_cast<uint32_t>(my_col) << 16) | ((static_cast<uint32_t>(excl >> kShare) * 128u) >> 4));
-          }
-          __syncwarp();
           if (elect_one()) {
             starts[s] = off;
-            meta[s].nruns = __popc(run_starts);
-            meta[s].ksteps = ch_ksteps;
-            meta[s].a_off = off;
-            mbar_arrive_expect_tx(full, kPanelBytes + bytes);
+            mbar_arrive_expect_tx(full, kPanelBytes + bytes + tb_bytes);
             tma_load_2d(panels + s * kPanelBytes, &tmap_b, ch_k0, j0, full);
             for (uint32_t done = 0; done < bytes; done += 32768u) {
               const uint32_t piece = min(32768u, bytes - done);
               bulk_load(a_ring + off + done, src + done, piece, full);
             }
+            bulk_load(tables_u + s * kTableBytes, p.tables + static_cast<size_t>(tb_off16) * 16,
+                      tb_bytes, full);
             if (tr) trace_put(p, true, 0, rank, iss, tp0, sm_clock());
           }
+          __syncwarp();
           head = off + bytes;
           ++iss;
-          __syncwarp();
+          if (++iss_slot == static_cast<uint32_t>(P)) iss_slot = 0;
         }
       }
     }
   } else if (warp == 1) {
     if (kPair && rank != 0) {
       // ===================== peer CTA: forward "stage full" to the leader =====================
-      if (lane == 0) {
-        uint32_t use = 0;
-        const uint32_t remote = map_to_cta(bar_full, 0);
-        for (int it = it_begin; it < it_end; ++it) {
-          const SuperRow sr = p.srows[p.items[p.cta_items[it]].srow];
-          for (int c = 0; c < sr.chunk_count; ++c, ++use) {
-            const uint32_t s = use % P;
-            mbar_wait(bar_full + 8 * s, (use / P) & 1, 6);
-            mbar_arrive_remote(remote + 8 * s);
-          }
+      const uint32_t remote = map_to_cta(bar_full, 0);
+      uint32_t slot = 0, phase = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        const int chunk_count = p.srows[p.items[p.cta_items[it]].srow].chunk_count;
+        for (int c = 0; c < chunk_count; ++c) {
+          mbar_wait(bar_full + 8 * slot, phase, 6);
+          if (lane == 0) mbar_arrive_remote(remote + 8 * slot);
+          __syncwarp();
+          if (++slot == static_cast<uint32_t>(P)) { slot = 0; phase ^= 1u; }
         }
       }
     } else {
       // ===================== MMA issuer (leader CTA, converged warp) =====================
-      uint32_t use = 0;        // pipeline uses consumed
+      uint32_t use = 0, slot = 0, phase = 0;
       uint32_t acc_use[2] = {0, 0};
       int local = 0;
       for (int it = it_begin; it < it_end; ++it, ++local) {
@@ -468,17 +435,17 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
         tc_fence_after();
         const uint32_t acc_base = tmem_base + as * p.acc_stage_cols;
         for (int c = 0; c < chunk_count; ++c, ++use) {
-          const uint32_t s = use % P;
-          mbar_wait(bar_full + 8 * s, (use / P) & 1, 4);   // pair: own half AND the peer's relay
+          const uint32_t s = slot;
+          mbar_wait(bar_full + 8 * s, phase, 4);   // pair: own half AND the peer's relay
           const unsigned long long tm0 = tr ? sm_clock() : 0ull;
           tc_fence_after();
-          const StageMeta* mt = meta + s;
-          const uint4 hdr = *reinterpret_cast<const uint4*>(mt);   // nruns, ksteps, a_off
+          const uint8_t* tbl = tables_s + s * kTableBytes;
+          const uint2 hdr = *reinterpret_cast<const uint2*>(tbl);   // nruns, ksteps
           const int nruns = static_cast<int>(hdr.x);
           const int ksteps = static_cast<int>(hdr.y);
           uint2 rec = make_uint2(0u, 0u);
-          if (lane < nruns) rec = mt->run[lane];
-          const uint32_t a_base = a_ring + hdr.z;
+          if (lane < nruns) rec = *reinterpret_cast<const uint2*>(tbl + 16 + 8 * lane);
+          const uint32_t a_base = a_ring + starts[s];
           const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
           for (int r = 0; r < nruns; ++r) {
             const uint32_t idesc = __shfl_sync(0xFFFFFFFFu, rec.x, r);
@@ -500,6 +467,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             trace_put(p, true, 1, 0, use, tm0, tm0);
             trace_put(p, true, 1, 1, use, tm0, sm_clock());
           }
+          if (++slot == static_cast<uint32_t>(P)) { slot = 0; phase ^= 1u; }
         }
         if (elect_one()) tc_commit<kPair>(bar_acc_full + 8 * as);
         __syncwarp();

@@ -14,12 +14,12 @@ struct SpmmParams {
   const Segment*  segs;
   const Chunk*    chunks;
   const uint8_t*  a_packed;     // packed A images (see PackJob)
+  const uint8_t*  tables;       // run tables of all chunks (sched_types.h)
   float*          C;
   int64_t         c_sr;         // element stride of C between rows
   int64_t         c_sj;         // element stride of C between columns
   int32_t         n;            // columns of B and C
   int32_t         accumulate;   // 1: C += A*B (reference beta = 1), 0: C = A*B
-  uint32_t        idesc_base;   // tcgen05 instruction descriptor, N field empty
   int32_t         kind_tf32;    // 0: kind::f16 (bf16/fp16), 1: kind::tf32
   int32_t         panel_stages; // pipeline depth (<= 8)
   int32_t         a_ring_bytes; // bytes of the A-image ring (multiple of 1024)

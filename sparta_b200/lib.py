@@ -260,13 +260,14 @@ SEG_DT = np.dtype([("c_row0", "<i4"), ("h", "<i4"), ("h_pad", "<i4"), ("tmem_col
 SROW_DT = np.dtype([("seg_begin", "<i4"), ("seg_count", "<i4"), ("chunk_begin", "<i4"),
                     ("chunk_count", "<i4"), ("n_cols", "<i4"), ("break_mask", "<u4"), ("pad", "<i4", (2,))])
 CHUNK_DT = np.dtype([("k0", "<i4"), ("mask", "<u4"), ("a_off16", "<u4"), ("a_bytes", "<u4"),
-                     ("ksteps", "<i4"), ("pad", "<i4", (3,))])
+                     ("ksteps", "<i4"), ("tbl_bytes", "<u4"), ("tbl_off16", "<u4"),
+                     ("pad", "<i4")])
 ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4")])
 JOB_DT = np.dtype([("src_base", "<i8"), ("src_rs", "<i8"), ("src_ks", "<i8"), ("h", "<i4"),
                    ("h_pad", "<i4"), ("k_lo", "<i4"), ("k_w", "<i4"), ("dst_off16", "<u4"),
                    ("pad", "<i4", (3,))])
-_PLAN_DTYPES = [SEG_DT, SROW_DT, CHUNK_DT, ITEM_DT, np.dtype("<i4"), np.dtype("<i4"), JOB_DT]
-_PLAN_NAMES = ["segs", "srows", "chunks", "items", "cta_ptr", "cta_items", "jobs"]
+_PLAN_DTYPES = [SEG_DT, SROW_DT, CHUNK_DT, ITEM_DT, np.dtype("<i4"), np.dtype("<i4"), JOB_DT, np.dtype("<u4")]
+_PLAN_NAMES = ["segs", "srows", "chunks", "items", "cta_ptr", "cta_items", "jobs", "tables"]
 
 
 def vbr_plan(rows, cols, block_col_size, row_part, nzcount, jab, n, **opts):

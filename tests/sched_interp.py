@@ -83,17 +83,27 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
                         panel[:jj, :kk] = Bm[j0:j0 + jj, k0:k0 + kk]
                     kuse = int(ch["ksteps"]) * kstep
                     share16 = int(ch["a_bytes"]) // nshare // 16
-                    cursor = [int(ch["a_off16"]) + c * share16 for c in range(nshare)]
                     used = 0
-                    for (mb, me, N) in runs_of(int(ch["mask"]), int(sr["break_mask"]), tcols):
-                        assert N % 16 == 0 and N <= 256
+                    # the run table is what the MMA warp executes; it must agree with the run rule
+                    t0 = int(ch["tbl_off16"]) * 4
+                    tbl = plan["tables"][t0:t0 + int(ch["tbl_bytes"]) // 4]
+                    expect = runs_of(int(ch["mask"]), int(sr["break_mask"]), tcols)
+                    assert int(tbl[0]) == len(expect) and int(tbl[1]) == int(ch["ksteps"])
+                    assert int(ch["tbl_bytes"]) % 16 == 0 and int(ch["tbl_bytes"]) >= 16 + 8 * len(expect)
+                    for r, (mb, me, N_expect) in enumerate(expect):
+                        idesc, where = int(tbl[4 + 2 * r]), int(tbl[5 + 2 * r])
+                        N = ((idesc >> 17) & 0x3F) << 3
+                        assert N == N_expect and N % 16 == 0 and N <= 256
+                        assert ((idesc >> 24) & 0x1F) << 4 == 128 * nshare          # MMA M
+                        assert (idesc >> 7) & 7 == (idesc >> 10) & 7 == {2: 1, 4: 2}[esize] or esize == 2
+                        col, off16 = where >> 16, where & 0xFFFF
+                        assert col == tcols[mb]
                         half = N // nshare
                         parts = []
                         for c in range(nshare):   # the MMA reads N/nshare rows from each CTA's smem
-                            parts.append(read_image(store, cursor[c], half, esize))
-                            cursor[c] += half * 8
+                            parts.append(read_image(store, int(ch["a_off16"]) + c * share16 + off16, half, esize))
                         img = np.concatenate(parts, axis=0)
-                        acc[:, tcols[mb]:tcols[mb] + N] += panel[:, :kuse] @ img[:, :kuse].T
+                        acc[:, col:col + N] += panel[:, :kuse] @ img[:, :kuse].T
                         used += N * 128
                     assert used == int(ch["a_bytes"])
                 for sg in sg_all:

@@ -130,5 +130,10 @@ def test_oracle_equals_reference_build(oracle, reference, tmp_path, kind, flags)
         else:
             assert a == b or (a != a and b != b), k
     rng = np.random.default_rng(0)
-    B = rng.uniform(0, 1, size=(3, int(rr["cols"]))).astype(np.float32)
+    # VBR::multiply reads B[w*jb + k + j*cols] for k < w even in the last, ragged column block
+    # (vbr.cpp:362), i.e. up to w-1 floats past the end of the last column of B; the matching A
+    # entries are zero.  Give the buffer that much finite slack so 0 * garbage cannot make NaNs.
+    cols, w = int(rr["cols"]), int(rr["block_col_size"])
+    B = np.zeros(3 * cols + w, dtype=np.float32)
+    B[:3 * cols] = rng.uniform(0, 1, size=3 * cols)
     assert np.array_equal(oracle.vbr_multiply(rr, B, 3), reference.vbr_multiply(rr, B, 3))
