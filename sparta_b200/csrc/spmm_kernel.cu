@@ -77,6 +77,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
+// Relaxed flavour for the per-chunk "my half has landed" relay: the data it announces was written
+// by TMA and is read by tcgen05.mma (both async proxy, ordered by the mbarrier itself), so no
+// generic-proxy release is needed -- and a cluster-scope release costs a full memory barrier
+// (ERRBAR/MEMBAR, ~2000 cycles per chunk in the first pair-mode trace).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -414,7 +422,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
         const int chunk_count = p.srows[p.items[p.cta_items[it]].srow].chunk_count;
         for (int c = 0; c < chunk_count; ++c) {
           mbar_wait(bar_full + 8 * slot, phase, 6);
-          if (lane == 0) mbar_arrive_remote(remote + 8 * slot);
+          if (lane == 0) mbar_arrive_remote_relaxed(remote + 8 * slot);
           __syncwarp();
           if (++slot == static_cast<uint32_t>(P)) { slot = 0; phase ^= 1u; }
         }
@@ -490,8 +498,8 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
         mbar_arrive(bar_acc_empty);
         if (p.acc_stages == 2) mbar_arrive(bar_acc_empty + 8);
       } else {
-        mbar_arrive_remote(acc_empty_remote);
-        if (p.acc_stages == 2) mbar_arrive_remote(acc_empty_remote + 8);
+        mbar_arrive_remote_relaxed(acc_empty_remote);
+        if (p.acc_stages == 2) mbar_arrive_remote_relaxed(acc_empty_remote + 8);
       }
     }
     uint32_t acc_use[2] = {0, 0};
@@ -550,7 +558,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       __syncwarp();
       if (lane == 0) {
         if (rank == 0) mbar_arrive(bar_acc_empty + 8 * as);
-        else mbar_arrive_remote(acc_empty_remote + 8 * as);
+        else mbar_arrive_remote_relaxed(acc_empty_remote + 8 * as);   // TMEM is ordered by tcgen05 fences
         if (tr && warp == 2) trace_put(p, true, 2, rank, static_cast<uint32_t>(local), te0, sm_clock());
       }
     }
