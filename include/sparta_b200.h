@@ -53,7 +53,7 @@ typedef struct sparta_options {
   int32_t accumulate;    /* 0: C := A*B (default) ; 1: C += A*B */
   int32_t seg_rows;      /* max rows per MMA segment, multiple of 16 <= 256 (default 64) */
   int32_t acc_cols;      /* TMEM columns per accumulator stage: 512 (default, one stage) or 256 (two) */
-  int32_t panel_stages;  /* smem pipeline depth, 2..8 (default 4) */
+  int32_t panel_stages;  /* smem pipeline depth, 2..8 (default 5) */
   int32_t num_ctas;      /* persistent grid size (default: SM count) */
   int64_t block_row_begin; /* shard: first block-row (default 0) */
   int64_t block_row_end;   /* shard: one past the last block-row (default: all) */

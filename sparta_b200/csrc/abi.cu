@@ -86,7 +86,7 @@ static void resolve_options(const sparta_options* in, sparta_options* o) {
   if (o->seg_rows == 0) o->seg_rows = 64;
   if (o->acc_cols == 0) o->acc_cols = 512;
   if (o->l2_slab_mb <= 0) o->l2_slab_mb = 80;
-  if (o->panel_stages == 0) o->panel_stages = 4;
+  if (o->panel_stages == 0) o->panel_stages = 5;
 }
 
 static int ring_bytes_for(int panel_stages) {

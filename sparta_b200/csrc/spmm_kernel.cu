@@ -447,29 +447,41 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
           mbar_wait(bar_full + 8 * s, phase, 4);   // pair: own half AND the peer's relay
           const unsigned long long tm0 = tr ? sm_clock() : 0ull;
           tc_fence_after();
-          const uint8_t* tbl = tables_s + s * kTableBytes;
-          const uint2 hdr = *reinterpret_cast<const uint2*>(tbl);   // nruns, ksteps
-          const int nruns = static_cast<int>(hdr.x);
-          const int ksteps = static_cast<int>(hdr.y);
-          uint2 rec = make_uint2(0u, 0u);
-          if (lane < nruns) rec = *reinterpret_cast<const uint2*>(tbl + 16 + 8 * lane);
-          const uint32_t a_base = a_ring + starts[s];
-          const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
-          for (int r = 0; r < nruns; ++r) {
-            const uint32_t idesc = __shfl_sync(0xFFFFFFFFu, rec.x, r);
-            const uint32_t where = __shfl_sync(0xFFFFFFFFu, rec.y, r);
-            const uint64_t adesc = smem_desc(a_base + ((where & 0xFFFFu) << 4));
-            const uint32_t d_tmem = acc_base + (where >> 16);
-            if (elect_one()) {
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                // +32 bytes along K inside the 128-byte swizzle row
-                tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
+          // One elected lane does the whole chunk: it reads the host-decoded run table the copy
+          // engine placed in this stage, fires ksteps MMAs per run and commits.  Staying inside a
+          // single elect region keeps every operand on the uniform datapath and avoids a
+          // shuffle / re-election per run.
+          if (elect_one()) {
+            const uint4* tbl = reinterpret_cast<const uint4*>(tables_s + s * kTableBytes);
+            const uint4 hdr = tbl[0];            // nruns, ksteps
+            const uint4 r01 = tbl[1];            // runs 0 and 1: {idesc, where} x 2
+            const uint4 r23 = tbl[2];            // runs 2 and 3 (slot is always kTableBytes long)
+            const uint32_t a_base = a_ring + starts[s];
+            const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
+            const int nruns = static_cast<int>(hdr.x);
+            const int ksteps = static_cast<int>(hdr.y);
+            auto fire = [&](uint32_t idesc, uint32_t where) {
+              const uint64_t adesc = smem_desc(a_base + ((where & 0xFFFFu) << 4));
+              const uint32_t d_tmem = acc_base + (where >> 16);
+              if (ksteps == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle row
+                  tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
+              } else {
+                for (int k = 0; k < ksteps; ++k)
+                  tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
               }
+            };
+            fire(r01.x, r01.y);
+            if (nruns > 1) fire(r01.z, r01.w);
+            if (nruns > 2) fire(r23.x, r23.y);
+            if (nruns > 3) fire(r23.z, r23.w);
+            for (int r = 4; r < nruns; ++r) {
+              const uint2 rr = *reinterpret_cast<const uint2*>(tables_s + s * kTableBytes + 16 + 8 * r);
+              fire(rr.x, rr.y);
             }
-            __syncwarp();
+            tc_commit<kPair>(bar_empty + 8 * s);
           }
-          if (elect_one()) tc_commit<kPair>(bar_empty + 8 * s);
           __syncwarp();
           if (tr && lane == 0) {   // rank-0 slot: stage seen full; rank-1 slot: {seen full, MMAs issued}
             trace_put(p, true, 1, 0, use, tm0, tm0);
