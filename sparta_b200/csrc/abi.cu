@@ -6,6 +6,8 @@
 // device state lives in a handle so warm-up and repetitions reuse it.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -207,6 +209,8 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   if (major != 10)
     return fail(SPARTA_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)");
 
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;
+  const auto tc0 = std::chrono::steady_clock::now();
   sparta_handle* h = new sparta_handle();
   h->device = dev;
   h->sopt.precision = o.precision;
@@ -241,6 +245,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
     if (e_ != cudaSuccess) { free_handle(h); return fail_cuda(e_, #call); }    \
   } while (0)
 
+  const auto tc1 = std::chrono::steady_clock::now();
   H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   H_TRY(cudaEventCreate(&h->ev0));
   H_TRY(cudaEventCreate(&h->ev1));
@@ -277,6 +282,10 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->upload_ms = ms;
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
+  if (timing)
+    fprintf(stderr, "sparta create: host schedule %.1f ms, device alloc + upload + repack %.1f ms (GPU-side events %.1f ms)\n",
+            std::chrono::duration<double, std::milli>(tc1 - tc0).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc1).count(), ms);
 #undef H_TRY
   *out = h;
   return SPARTA_OK;
@@ -568,13 +577,26 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
   o.struct_size = sizeof(o);
   o.precision = precision;
   sparta_handle* h = nullptr;
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;   // phase breakdown of the one-shot call on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   int rc = sparta_vbr_create(&h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o);
   if (rc) return rc;
+  const auto t1 = now();
   rc = sparta_set_B(h, B, ldb, n, 0);
+  const auto t2 = now();
   if (!rc) rc = sparta_run(h, dt_ms);
+  const auto t3 = now();
   if (!rc) rc = sparta_get_C(h, C, ldc, 0);
+  const auto t4 = now();
   const std::string keep = g_last_error;
   sparta_destroy(h);
+  if (timing)
+    fprintf(stderr, "sparta_vbr_spmm: create %.1f ms (schedule + A upload + repack), set_B %.1f, run %.1f, get_C %.1f, destroy %.1f\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
   if (rc) g_last_error = keep;
   return rc;
 }
