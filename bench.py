@@ -431,7 +431,7 @@ def run_ours(args, wl):
 
 def tuning_opts(args):
     o = {}
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain"):
         val = getattr(args, k)
         if val:
             o[k] = val
@@ -569,7 +569,7 @@ def main():
     ap.add_argument("--cpu-gflop-per-step", type=float, default=8.0,
                     help="--impl reference: nonzero-block GFLOP per thread-step sample")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain"):
         ap.add_argument("--" + k.replace("_", "-"), dest=k, type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -60,7 +60,10 @@ typedef struct sparta_options {
   int32_t cta_pair;      /* 0/2: CTA pairs, tcgen05 cta_group::2, 256-column tiles (default); 1: single CTAs */
   int32_t row_order;     /* 0/2: super-rows group block-rows of similar block count (default); 1: input order */
   int32_t l2_slab_mb;    /* B columns kept L2-resident per pass, in MiB of B (default 80) */
-  int32_t reserved[5];
+  int32_t max_chain;     /* longest run of tcgen05.mma accumulations into one TMEM accumulator before the
+                            partial sum is drained and added to C in fp32 by the epilogue; 0 = the
+                            precision's default (tf32: 128, bf16/fp16: unlimited), -1 = unlimited */
+  int32_t reserved[4];
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */
@@ -108,6 +111,16 @@ int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols,
                            int64_t ell_blocksize, int64_t ellColInd_rows,
                            int64_t ellColInd_cols, const int64_t* ellColInd,
                            const float* ellValues, const sparta_options* opt);
+
+/* A as a flat CSR (rowptr[rows+1], colind ascending inside a row, val or NULL for a pattern-only
+ * matrix whose entries are all 1) -- what prepare_cusparse_CSR (cuda_utilities.cpp:1433-1477)
+ * flattens the reference's CSR struct into, with int64 indices.  B and C default to ROW_MAJOR like
+ * the reference's cuSPARSE call (:1346-1355).  The options' block_row_begin / block_row_end select
+ * a range of ROWS.  SPARTA_TF32 selects plain fp32 arithmetic here (no tensor cores on this
+ * path): that mode is bit-identical to CSR::multiply (src/general/csr.cpp:49-65).
+ * Replaces the upload half of cusparse_gemm_custom (cuda_utilities.cpp:1251-1431, -M 2). */
+int sparta_csr_create(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                      const int64_t* colind, const float* val, const sparta_options* opt);
 
 /* Dense operand B (cols x n fp32).  ld: leading dimension in elements (>= cols for
  * COL_MAJOR, >= n for ROW_MAJOR).  on_device != 0: B is a device pointer on the
@@ -162,6 +175,18 @@ int sparta_bellpack_spmm(int64_t rows, int64_t cols, int64_t ell_blocksize,
                          const int64_t* ellColInd, const float* ellValues, const float* B,
                          int64_t ldb, int64_t n, float* C, int64_t ldc, int precision,
                          float* dt_ms);
+
+/* Replaces cusparse_blockmat_multiplyAB (cuda_utilities.cpp:1479-1493, -M 2): flat CSR in,
+ * B and C row-major. */
+int sparta_csr_spmm(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
+                    const float* val, const float* B, int64_t ldb, int64_t n, float* C, int64_t ldc,
+                    int precision, float* dt_ms);
+
+/* Device buffers are taken from the device's stream-ordered memory pool and stay cached there
+ * after sparta_destroy / a one-shot call, so that repeated calls do not pay cudaMalloc / cudaFree
+ * (the reference re-allocates on every call, cuda_utilities.cpp:95-98,204-206).  This returns the
+ * cached memory of every device the library has used to the driver. */
+int sparta_release_workspace(void);
 
 /* ---- host-side helpers (no GPU needed) ---- */
 

@@ -6,6 +6,7 @@
 // -lcublas -lcusparse and CUTLASS.  test/cuda/cuda_multiply.cpp then builds UNCHANGED and its
 // -M switch (include/definitions.h:19) runs on the sm_100a kernel family:
 //
+//   -M 2  cusparse_spmm          cusparse_blockmat_multiplyAB      -> sparta_csr_spmm      (fp32)
 //   -M 3  cusparse_bellpack      bellpack_blockmat_multiplyAB      -> sparta_bellpack_spmm (fp16)
 //   -M 4  cublas_vbr             cublas_fixed_blocks_multiply      -> sparta_vbr_spmm      (fp16)
 //   -M 7  cublas_vbr_batched     cublas_blockmat_batched           -> sparta_vbr_spmm      (tf32)
@@ -20,10 +21,11 @@
 // the compute only, any failure prints and exits like checkCudaErrors (helper_cuda.h:714-727).
 //
 // Not provided (outside the hot path): the inverted product C = B*A (-M 6, 11,
-// 12), CSR SpMM (-M 2) and the dense GEMMs (-M 1, 9); they print a message and exit.
+// 12) and the dense GEMMs (-M 1, 9); they print a message and exit.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "cuda_utilities.h"
 #include "cutlass_bellpack_lib.h"
@@ -138,6 +140,26 @@ void bellpack_cutlass_multiplyAB(VBR* A, DataT* B, int B_cols, DataT_C* C, int C
   bellpack_blockmat_multiplyAB(A, B, B_cols, C, C_cols, dt, verbose);
 }
 
+// ---- CSR x dense (B and C row-major, cuda_utilities.cpp:1346-1355) ------------------------------
+
+// prepare_cusparse_CSR (cuda_utilities.cpp:1433-1477) flattens the reference's array-of-rows CSR
+// into rowptr / colind / val; the same flattening here, with the ABI's int64 indices.  The
+// reference asks cuSPARSE for CUDA_R_32F compute (:1267), hence the fp32 default.
+void cusparse_blockmat_multiplyAB(CSR& A, DataT* B, int B_cols, DataT_C* C, int C_cols, float& dt) {
+  std::vector<int64_t> rowptr(static_cast<size_t>(A.rows) + 1, 0);
+  for (intT i = 0; i < A.rows; ++i) rowptr[i + 1] = rowptr[i] + A.nzcount[i];
+  std::vector<int64_t> colind(static_cast<size_t>(rowptr[A.rows]));
+  std::vector<float> val(A.pattern_only ? 0 : colind.size());
+  for (intT i = 0; i < A.rows; ++i)
+    for (intT q = 0; q < A.nzcount[i]; ++q) {
+      colind[rowptr[i] + q] = A.ja[i][q];
+      if (!A.pattern_only) val[rowptr[i] + q] = A.ma[i][q];
+    }
+  if (sparta_csr_spmm(A.rows, A.cols, rowptr.data(), colind.data(), A.pattern_only ? nullptr : val.data(), B, B_cols,
+                      B_cols, C, C_cols, precision_or(SPARTA_TF32), &dt))
+    die("sparta_csr_spmm");
+}
+
 // ---- debug printers the CLI calls at -v 3 ------------------------------------------------------
 
 void pico_print_DnM(const char* Cname, int Cn, int Cm, DataT_C* C) {
@@ -154,7 +176,6 @@ void cublas_blockmat_multiplyBA(const VBR&, DataT*, int, DataT_C*, float&, int) 
 void cutlas_blockmat_multiplyBA(const VBR&, DataT*, int, DataT_C*, float&) { not_provided("cutlas_blockmat_multiplyBA", "-M 11"); }
 void cutlas_blockmat_multiplyBA_streams(const VBR&, DataT*, int, DataT_C*, float&, int) { not_provided("cutlas_blockmat_multiplyBA_streams", "-"); }
 void cutlas_blockmat_batched(const VBR&, DataT*, int, DataT_C*, float&) { not_provided("cutlas_blockmat_batched", "-M 12"); }
-void cusparse_blockmat_multiplyAB(CSR&, DataT*, int, DataT_C*, int, float&) { not_provided("cusparse_blockmat_multiplyAB", "-M 2"); }
 void cublas_dense_multiplyAB(int, int, DataT*, DataT*, int, DataT_C*, float&) { not_provided("cublas_dense_multiplyAB", "-M 1"); }
 int cutlass_dense_multiplyAB(int, int, DataT*, int, DataT*, float, float, DataT_C*, float&) { not_provided("cutlass_dense_multiplyAB", "-M 9"); }
 DataT* csr2dn(CSR&) { not_provided("csr2dn", "-M 1 / -M 9"); }

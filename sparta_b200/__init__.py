@@ -7,8 +7,8 @@ library or without a CUDA device raises.
 """
 from .lib import (BF16, FP16, TF32, COL_MAJOR, ROW_MAJOR, Handle, SpartaError, load,
                   partition_block_rows, vbr_plan)
-from .api import VBR, bellpack_from_vbr, bellpack_spmm, vbr_spmm
+from .api import VBR, bellpack_from_vbr, bellpack_spmm, csr_spmm, vbr_spmm
 
 __all__ = ["BF16", "FP16", "TF32", "COL_MAJOR", "ROW_MAJOR", "Handle", "SpartaError", "load",
            "partition_block_rows", "vbr_plan", "VBR", "vbr_spmm", "bellpack_spmm",
-           "bellpack_from_vbr"]
+           "bellpack_from_vbr", "csr_spmm"]

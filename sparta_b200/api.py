@@ -80,3 +80,21 @@ def bellpack_spmm(rows, cols, blocksize, ell_col_ind, ell_values, B, B_cols, pre
                                          _lib._ptr(ind), _lib._ptr(vals), _lib._ptr(B), B_cols,
                                          B_cols, _lib._ptr(Cbuf), B_cols, prec, C.byref(dt)))
     return Cbuf, dt.value
+
+
+def csr_spmm(rows, cols, rowptr, colind, val, B, B_cols, precision="bf16"):
+    """C = A*B like cusparse_blockmat_multiplyAB (reference cuda_utilities.cpp:1479-1493, `-M 2`):
+    A as the flat CSR prepare_cusparse_CSR builds (val=None for a pattern-only matrix), B and C
+    row-major.  precision "tf32" runs plain fp32 (bit-identical to CSR::multiply).  Returns (C, dt_ms)."""
+    lib = _lib.load()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    colind = np.ascontiguousarray(colind, dtype=np.int64)
+    val = None if val is None else np.ascontiguousarray(val, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    Cbuf = np.zeros((rows, B_cols), dtype=np.float32)
+    dt = C.c_float(0)
+    prec = _lib.PRECISIONS[precision]
+    _lib._check(lib.sparta_csr_spmm(rows, cols, _lib._ptr(rowptr), _lib._ptr(colind),
+                                    None if val is None else _lib._ptr(val), _lib._ptr(B), B_cols, B_cols,
+                                    _lib._ptr(Cbuf), B_cols, prec, C.byref(dt)))
+    return Cbuf, dt.value

@@ -12,11 +12,14 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sparta_b200.h"
 #include "blocking.h"
+#include "csr_kernel.h"
 #include "host_formats.h"
 #include "pack_kernels.h"
 #include "schedule.h"
@@ -40,6 +43,40 @@ static int fail_cuda(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return fail_cuda(e_, #call);     \
   } while (0)
 
+// ---- device memory: the stream-ordered allocator with a retained pool ------------------------
+// Every device buffer comes from the device's default memory pool (cudaMallocAsync) whose release
+// threshold is raised once per device so that freed blocks stay cached: the one-shot calls
+// (upload, multiply, download per call, like the reference's routines) then pay cudaMalloc /
+// cudaFree -- tens of milliseconds for multi-GB buffers, and a device-wide synchronisation
+// each -- only on their first use.  sparta_release_workspace() hands the cache back.
+static std::mutex g_pool_mutex;
+static bool g_pool_ready[64] = {};
+
+static cudaError_t pool_prepare(int dev) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (dev < 0 || dev >= 64 || g_pool_ready[dev]) return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, dev);
+  if (e != cudaSuccess) return e;
+  uint64_t keep = UINT64_MAX;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  if (e == cudaSuccess) g_pool_ready[dev] = true;
+  return e;
+}
+static cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t s) {
+  *p = nullptr;
+  return cudaMallocAsync(p, std::max<size_t>(bytes, 16), s);
+}
+template <class T>
+static cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t s) {
+  return dev_alloc(reinterpret_cast<void**>(p), bytes, s);
+}
+template <class T>
+static void dev_free(T*& p, cudaStream_t s) {
+  if (p) cudaFreeAsync(const_cast<void*>(reinterpret_cast<const void*>(p)), s);
+  p = nullptr;
+}
+
 struct sparta_host_vbr { HostVBR v; };
 struct sparta_host_bell { HostBell b; };
 
@@ -53,12 +90,15 @@ struct sparta_plan {
 
 struct sparta_handle {
   int device = 0;
+  int kind = 0;   // 0: block-sparse (VBR / Blocked-ELL) on the tcgen05 kernel, 1: CSR gather kernel
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t up0 = nullptr, up1 = nullptr;   // around the last upload (create / set_B)
   ScheduleOptions sopt;
   int b_row_major = 0, c_row_major = 0, accumulate = 0;
   int panel_stages = 4, a_ring_bytes = 0;
   int64_t cols = 0, block_rows = 0, w = 0;
+  int64_t rows = 0;   // C rows of the shard
   Structure st;   // jobs are dropped after packing
   Assignment as;
   Segment* d_segs = nullptr;
@@ -69,13 +109,18 @@ struct sparta_handle {
   Item* d_items = nullptr;
   int32_t* d_cta_ptr = nullptr;
   int32_t* d_cta_items = nullptr;
+  // CSR handles
+  int64_t* d_rowptr = nullptr;
+  int32_t* d_colind = nullptr;
+  float* d_val = nullptr;
+  int32_t* d_row_order = nullptr;
+  int64_t nnz = 0, heavy_rows = 0;
   void* d_B = nullptr;
   size_t b_cap = 0;
   int64_t ldk = 0, n = 0;
   float* d_C = nullptr;
   size_t c_cap = 0;
   int64_t ldc = 0;
-  double upload_ms = 0;
   int64_t launches = 0;
 };
 
@@ -172,28 +217,32 @@ static const char* blockrows_from_bell(int64_t bs, int64_t ind_rows, int64_t ind
 static void free_handle(sparta_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->d_segs); cudaFree(h->d_srows); cudaFree(h->d_chunks); cudaFree(h->d_tables); cudaFree(h->d_a);
-  cudaFree(h->d_items); cudaFree(h->d_cta_ptr); cudaFree(h->d_cta_items);
-  cudaFree(h->d_B); cudaFree(h->d_C);
+  cudaStream_t s = h->stream;
+  if (s) {
+    dev_free(h->d_segs, s); dev_free(h->d_srows, s); dev_free(h->d_chunks, s); dev_free(h->d_tables, s);
+    dev_free(h->d_a, s); dev_free(h->d_items, s); dev_free(h->d_cta_ptr, s); dev_free(h->d_cta_items, s);
+    dev_free(h->d_rowptr, s); dev_free(h->d_colind, s); dev_free(h->d_val, s); dev_free(h->d_row_order, s);
+    dev_free(h->d_B, s); dev_free(h->d_C, s);
+    cudaStreamSynchronize(s);   // the blocks are back in the pool before the stream goes away
+  }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->up0) cudaEventDestroy(h->up0);
+  if (h->up1) cudaEventDestroy(h->up1);
+  if (s) cudaStreamDestroy(s);
   delete h;
 }
 
 template <class T>
 static cudaError_t upload_vec(const std::vector<T>& v, T** dptr, cudaStream_t s) {
-  *dptr = nullptr;
-  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), bytes);
+  cudaError_t e = dev_alloc(dptr, v.size() * sizeof(T), s);
   if (e != cudaSuccess) return e;
   if (!v.empty()) e = cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
   return e;
 }
 
-static int create_common(sparta_handle** out, BlockRows& br, const float* src_host,
-                         int64_t src_elems, int64_t cols, const sparta_options& o,
-                         int default_row_major) {
+// Device, stream and events of a new handle.  Returns SPARTA_OK or a failure code (handle freed).
+static int open_handle(sparta_handle** out, const sparta_options& o, int* sms_out) {
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -208,11 +257,37 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (major != 10)
     return fail(SPARTA_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)");
-
-  const bool timing = getenv("SPARTA_TIMING") != nullptr;
-  const auto tc0 = std::chrono::steady_clock::now();
+  if (o.precision < 0 || o.precision > 2) return fail(SPARTA_ERR_INVALID, "invalid precision");
+  CU_TRY(pool_prepare(dev));
   sparta_handle* h = new sparta_handle();
   h->device = dev;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->up0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->up1);
+  if (e != cudaSuccess) { free_handle(h); return fail_cuda(e, "stream / event creation"); }
+  *sms_out = sms;
+  *out = h;
+  return SPARTA_OK;
+}
+
+// The host tile scheduler (tens of milliseconds at 10^5 blocks) runs on its own thread WHILE the
+// fp32 source crosses PCIe; nothing on the device waits for the CPU afterwards except the small
+// schedule arrays.  No stream synchronisation happens here: the caller's next set_B / run /
+// get_C are enqueued behind the upload on the handle's stream.
+static int create_common(sparta_handle** out, BlockRows& br, const float* src_host,
+                         int64_t src_elems, int64_t cols, const sparta_options& o,
+                         int default_row_major, bool defer_sync = false) {
+  *out = nullptr;
+  if (o.panel_stages < 2 || o.panel_stages > kMaxPanelStages)
+    return fail(SPARTA_ERR_INVALID, "invalid panel_stages");
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;
+  const auto tc0 = std::chrono::steady_clock::now();
+  sparta_handle* h = nullptr;
+  int sms = 0;
+  const int rc = open_handle(&h, o, &sms);
+  if (rc) return rc;
   h->sopt.precision = o.precision;
   h->sopt.seg_rows = o.seg_rows;
   h->sopt.acc_cols = o.acc_cols;
@@ -220,6 +295,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->sopt.pair = o.cta_pair != 1;
   h->sopt.sort_rows = o.row_order != 1;
   h->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
+  h->sopt.max_chain = o.max_chain;
   h->panel_stages = o.panel_stages;
   h->a_ring_bytes = ring_bytes_for(o.panel_stages);
   h->accumulate = o.accumulate ? 1 : 0;
@@ -228,64 +304,61 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->cols = cols;
   h->w = br.w;
   h->block_rows = br.count();
-  if (o.precision < 0 || o.precision > 2 || o.panel_stages < 2 || o.panel_stages > kMaxPanelStages) {
-    delete h;
-    return fail(SPARTA_ERR_INVALID, "invalid precision or panel_stages");
-  }
-  const char* serr = build_structure(br, h->sopt, &h->st);
-  if (*serr) { delete h; return fail(SPARTA_ERR_INVALID, serr); }
-  if (static_cast<int64_t>(h->st.max_chunk_bytes) > h->a_ring_bytes) {
-    delete h;
-    return fail(SPARTA_ERR_INVALID, "a chunk's A images exceed the shared-memory ring; lower acc_cols or panel_stages");
-  }
+
+  const char* serr = "";
+  std::thread sched([&] { serr = build_structure(br, h->sopt, &h->st); });
 
 #define H_TRY(call)                                                            \
   do {                                                                         \
     cudaError_t e_ = (call);                                                   \
-    if (e_ != cudaSuccess) { free_handle(h); return fail_cuda(e_, #call); }    \
+    if (e_ != cudaSuccess) {                                                   \
+      if (sched.joinable()) sched.join();                                      \
+      cudaStreamSynchronize(h->stream);                                        \
+      if (d_src) cudaFreeAsync(d_src, h->stream);                              \
+      if (d_jobs) cudaFreeAsync(d_jobs, h->stream);                            \
+      free_handle(h);                                                          \
+      return fail_cuda(e_, #call);                                             \
+    }                                                                          \
   } while (0)
 
+  float* d_src = nullptr;
+  PackJob* d_jobs = nullptr;
+  H_TRY(cudaEventRecord(h->up0, h->stream));
+  if (src_elems > 0) {
+    // Stage the fp32 source on the device; it is repacked into MMA-ready images there.
+    H_TRY(dev_alloc(&d_src, static_cast<size_t>(src_elems) * sizeof(float), h->stream));
+    H_TRY(cudaMemcpyAsync(d_src, src_host, static_cast<size_t>(src_elems) * sizeof(float),
+                          cudaMemcpyHostToDevice, h->stream));
+  }
+  sched.join();
   const auto tc1 = std::chrono::steady_clock::now();
-  H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  H_TRY(cudaEventCreate(&h->ev0));
-  H_TRY(cudaEventCreate(&h->ev1));
-  cudaEvent_t t0, t1;
-  H_TRY(cudaEventCreate(&t0));
-  H_TRY(cudaEventCreate(&t1));
-  H_TRY(cudaEventRecord(t0, h->stream));
-
+  if (*serr || static_cast<int64_t>(h->st.max_chunk_bytes) > h->a_ring_bytes) {
+    cudaStreamSynchronize(h->stream);
+    if (d_src) cudaFreeAsync(d_src, h->stream);
+    free_handle(h);
+    return fail(SPARTA_ERR_INVALID, *serr ? serr
+                : "a chunk's A images exceed the shared-memory ring; lower acc_cols or panel_stages");
+  }
+  h->rows = h->st.rows;
   H_TRY(upload_vec(h->st.segs, &h->d_segs, h->stream));
   H_TRY(upload_vec(h->st.srows, &h->d_srows, h->stream));
   H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
   H_TRY(upload_vec(h->st.tables, &h->d_tables, h->stream));
-  H_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_a), std::max<uint64_t>(h->st.a_bytes, 16)));
-
+  H_TRY(dev_alloc(&h->d_a, h->st.a_bytes, h->stream));
   if (!h->st.jobs.empty()) {
-    // Stage the fp32 source on the device, pack it into MMA-ready images there.
-    float* d_src = nullptr;
-    PackJob* d_jobs = nullptr;
-    H_TRY(cudaMalloc(reinterpret_cast<void**>(&d_src), std::max<int64_t>(src_elems, 1) * sizeof(float)));
-    cudaError_t e = cudaMemcpyAsync(d_src, src_host, src_elems * sizeof(float), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = upload_vec(h->st.jobs, &d_jobs, h->stream);
-    if (e == cudaSuccess)
-      e = pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_src);
-    cudaFree(d_jobs);
-    if (e != cudaSuccess) { free_handle(h); return fail_cuda(e, "A upload / pack"); }
+    H_TRY(upload_vec(h->st.jobs, &d_jobs, h->stream));
+    H_TRY(pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream));
   }
-  std::vector<PackJob>().swap(h->st.jobs);
-  H_TRY(cudaEventRecord(t1, h->stream));
-  H_TRY(cudaEventSynchronize(t1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, t0, t1);
-  h->upload_ms = ms;
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
+  dev_free(d_src, h->stream);
+  dev_free(d_jobs, h->stream);
+  std::vector<PackJob>().swap(h->st.jobs);   // pageable copies are staged before cudaMemcpyAsync returns
+  H_TRY(cudaEventRecord(h->up1, h->stream));
+  // The public create returns only when the caller's arrays are no longer being read.
+  if (!defer_sync) H_TRY(cudaStreamSynchronize(h->stream));
   if (timing)
-    fprintf(stderr, "sparta create: host schedule %.1f ms, device alloc + upload + repack %.1f ms (GPU-side events %.1f ms)\n",
+    fprintf(stderr, "sparta create: host schedule + enqueue of the A upload %.1f ms, enqueue of the rest %.1f ms\n",
             std::chrono::duration<double, std::milli>(tc1 - tc0).count(),
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc1).count(), ms);
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc1).count());
 #undef H_TRY
   *out = h;
   return SPARTA_OK;
@@ -309,9 +382,10 @@ int sparta_device_count(void) {
   return ok;
 }
 
-int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
-                      int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
-                      const int64_t* jab, const float* mab, const sparta_options* opt) {
+static int vbr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                           int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                           const int64_t* jab, const float* mab, const sparta_options* opt,
+                           bool defer_sync) {
   if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (rows < 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part || (block_rows && !nzcount))
@@ -330,13 +404,19 @@ int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t b
   for (int64_t jb : br.col)
     if (jb >= bc) return fail(SPARTA_ERR_INVALID, "jab entry beyond the last column block");
   if (src_hi > src_lo && !mab) return fail(SPARTA_ERR_INVALID, "mab is NULL");
-  return create_common(out, br, mab ? mab + src_lo : nullptr, src_hi - src_lo, cols, o, 0);
+  return create_common(out, br, mab ? mab + src_lo : nullptr, src_hi - src_lo, cols, o, 0, defer_sync);
 }
 
-int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t ell_blocksize,
-                           int64_t ellColInd_rows, int64_t ellColInd_cols,
-                           const int64_t* ellColInd, const float* ellValues,
-                           const sparta_options* opt) {
+int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                      int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                      const int64_t* jab, const float* mab, const sparta_options* opt) {
+  return vbr_create_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false);
+}
+
+static int bellpack_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t ell_blocksize,
+                                int64_t ellColInd_rows, int64_t ellColInd_cols,
+                                const int64_t* ellColInd, const float* ellValues,
+                                const sparta_options* opt, bool defer_sync) {
   if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (ell_blocksize <= 0 || rows < 0 || cols <= 0 || ellColInd_rows < 0 || ellColInd_cols < 0)
@@ -356,26 +436,117 @@ int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols, int6
   if (*e) return fail(SPARTA_ERR_INVALID, e);
   for (int64_t jb : br.col)
     if (jb >= cols / ell_blocksize) return fail(SPARTA_ERR_INVALID, "ellColInd entry beyond the last column block");
-  return create_common(out, br, ellValues ? ellValues + src_lo : nullptr, src_hi - src_lo, cols, o, 1);
+  return create_common(out, br, ellValues ? ellValues + src_lo : nullptr, src_hi - src_lo, cols, o, 1, defer_sync);
 }
 
-int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device) {
+int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t ell_blocksize,
+                           int64_t ellColInd_rows, int64_t ellColInd_cols,
+                           const int64_t* ellColInd, const float* ellValues,
+                           const sparta_options* opt) {
+  return bellpack_create_impl(out, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd,
+                              ellValues, opt, false);
+}
+
+// CSR handles: rows of the shard [row_begin, row_end) (block_row_begin / block_row_end of the
+// options count ROWS here).  Index arrays are narrowed to int32 columns on the host while the
+// values cross PCIe; the row order (descending nnz, stable) is the kernel's work list.
+static int csr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                           const int64_t* colind, const float* val, const sparta_options* opt,
+                           bool defer_sync) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows < 0 || cols <= 0 || !rowptr || (rows && rowptr[rows] > rowptr[0] && !colind))
+    return fail(SPARTA_ERR_INVALID, "invalid CSR dimensions or NULL index arrays");
+  if (cols > INT32_MAX || rows > INT32_MAX) return fail(SPARTA_ERR_INVALID, "CSR dimensions exceed int32");
+  sparta_options o;
+  resolve_options(opt, &o);
+  const int64_t lo = o.block_row_begin;
+  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : rows;
+  if (lo < 0 || hi > rows || lo > hi) return fail(SPARTA_ERR_INVALID, "row range out of bounds");
+  for (int64_t i = lo; i < hi; ++i)
+    if (rowptr[i + 1] < rowptr[i]) return fail(SPARTA_ERR_INVALID, "rowptr must be non-decreasing");
+  const int64_t p0 = rowptr[lo], nnz = rowptr[hi] - rowptr[lo], nrows = hi - lo;
+  sparta_handle* h = nullptr;
+  int sms = 0;
+  const int rc = open_handle(&h, o, &sms);
+  if (rc) return rc;
+  h->kind = 1;
+  h->sopt.precision = o.precision;
+  h->accumulate = o.accumulate ? 1 : 0;
+  h->b_row_major = o.b_layout == SPARTA_LAYOUT_DEFAULT ? 1 : (o.b_layout == SPARTA_ROW_MAJOR);
+  h->c_row_major = o.c_layout == SPARTA_LAYOUT_DEFAULT ? 1 : (o.c_layout == SPARTA_ROW_MAJOR);
+  h->cols = cols;
+  h->rows = nrows;
+  h->nnz = nnz;
+  h->block_rows = nrows;
+  h->w = 1;
+  h->st.rows = nrows;
+  h->st.nztot = nnz;
+  h->st.n_blocks = nnz;
+#define H_TRY(call)                                                            \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) { free_handle(h); return fail_cuda(e_, #call); }    \
+  } while (0)
+  H_TRY(cudaEventRecord(h->up0, h->stream));
+  H_TRY(dev_alloc(&h->d_val, static_cast<size_t>(nnz) * sizeof(float), h->stream));
+  std::vector<float> ones;
+  if (nnz > 0) {
+    if (val) {
+      H_TRY(cudaMemcpyAsync(h->d_val, val + p0, static_cast<size_t>(nnz) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else {   // pattern-only: every entry is 1 (csr.cpp:59)
+      ones.assign(static_cast<size_t>(nnz), 1.f);
+      H_TRY(cudaMemcpyAsync(h->d_val, ones.data(), static_cast<size_t>(nnz) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  std::vector<int32_t> col32(static_cast<size_t>(nnz));
+  for (int64_t q = 0; q < nnz; ++q) {
+    const int64_t c = colind[p0 + q];
+    if (c < 0 || c >= cols) { free_handle(h); return fail(SPARTA_ERR_INVALID, "column index out of range"); }
+    col32[static_cast<size_t>(q)] = static_cast<int32_t>(c);
+  }
+  std::vector<int64_t> ptr(static_cast<size_t>(nrows) + 1);
+  for (int64_t i = 0; i <= nrows; ++i) ptr[static_cast<size_t>(i)] = rowptr[lo + i] - p0;
+  std::vector<int32_t> order(static_cast<size_t>(nrows));
+  for (int64_t i = 0; i < nrows; ++i) order[static_cast<size_t>(i)] = static_cast<int32_t>(i);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
+  });
+  h->heavy_rows = 0;
+  while (h->heavy_rows < nrows && ptr[order[h->heavy_rows] + 1] - ptr[order[h->heavy_rows]] > kCsrHeavyNnz)
+    ++h->heavy_rows;
+  H_TRY(upload_vec(col32, &h->d_colind, h->stream));
+  H_TRY(upload_vec(ptr, &h->d_rowptr, h->stream));
+  H_TRY(upload_vec(order, &h->d_row_order, h->stream));
+  H_TRY(cudaEventRecord(h->up1, h->stream));
+  if (!defer_sync || !val) H_TRY(cudaStreamSynchronize(h->stream));
+#undef H_TRY
+  *out = h;
+  return SPARTA_OK;
+}
+
+int sparta_csr_create(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                      const int64_t* colind, const float* val, const sparta_options* opt) {
+  return csr_create_impl(out, rows, cols, rowptr, colind, val, opt, false);
+}
+
+static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device,
+                      bool defer_sync) {
   if (!h || !B) return fail(SPARTA_ERR_INVALID, "NULL handle or B");
   if (n <= 0) return fail(SPARTA_ERR_INVALID, "n must be positive");
   const int64_t min_ld = h->b_row_major ? n : h->cols;
   if (ld < min_ld) return fail(SPARTA_ERR_INVALID, "leading dimension of B too small");
+  if (h->kind == 1 && n > (1 << 30)) return fail(SPARTA_ERR_INVALID, "n too large");
   CU_TRY(cudaSetDevice(h->device));
-  cudaEvent_t t0, t1;
-  CU_TRY(cudaEventCreate(&t0));
-  CU_TRY(cudaEventCreate(&t1));
-  CU_TRY(cudaEventRecord(t0, h->stream));
-  const int esize = prec_esize(h->sopt.precision);
-  const int64_t ldk = (h->cols + 63) / 64 * 64;
-  const size_t b_bytes = static_cast<size_t>(n) * ldk * esize;
+  CU_TRY(cudaEventRecord(h->up0, h->stream));
+  const int esize = (h->kind == 1 && h->sopt.precision == PREC_TF32) ? 4 : prec_esize(h->sopt.precision);
+  // block kernel: [n][ldk] k-contiguous;  CSR kernel: [cols][ldn] n-contiguous, ldn = n rounded to 8
+  const int64_t ldk = h->kind == 1 ? (n + 7) / 8 * 8 : (h->cols + 63) / 64 * 64;
+  const size_t b_bytes = static_cast<size_t>(h->kind == 1 ? h->cols : n) * ldk * esize;
   if (b_bytes > h->b_cap) {
-    cudaFree(h->d_B);
-    h->d_B = nullptr; h->b_cap = 0;
-    CU_TRY(cudaMalloc(&h->d_B, b_bytes));
+    dev_free(h->d_B, h->stream);
+    h->b_cap = 0;
+    CU_TRY(dev_alloc(&h->d_B, b_bytes, h->stream));
     h->b_cap = b_bytes;
   }
   h->ldk = ldk;
@@ -386,53 +557,62 @@ int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on
   if (!on_device) {
     const int64_t lines = h->b_row_major ? h->cols : n;     // number of ld-strided lines
     const int64_t width = h->b_row_major ? n : h->cols;     // contiguous elements per line
-    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&d_stage), static_cast<size_t>(lines) * width * sizeof(float)));
+    CU_TRY(dev_alloc(&d_stage, static_cast<size_t>(lines) * width * sizeof(float), h->stream));
     cudaError_t e = cudaMemcpy2DAsync(d_stage, width * sizeof(float), B, ld * sizeof(float),
                                       width * sizeof(float), lines, cudaMemcpyHostToDevice, h->stream);
-    if (e != cudaSuccess) { cudaFree(d_stage); return fail_cuda(e, "B upload"); }
+    if (e != cudaSuccess) { dev_free(d_stage, h->stream); return fail_cuda(e, "B upload"); }
     src = d_stage;
     src_ld = width;
   }
-  cudaError_t e = convert_b(src, src_ld, h->b_row_major, h->d_B, ldk, h->cols, n, h->sopt.precision, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_stage);
+  cudaError_t e;
+  if (h->kind == 1) {
+    // the CSR kernel wants rows of B contiguous: same converters with the roles of the two
+    // dimensions exchanged (a row-major source needs no transpose here), zero-filled padding
+    if (ldk != n) e = cudaMemsetAsync(h->d_B, 0, b_bytes, h->stream); else e = cudaSuccess;
+    if (e == cudaSuccess)
+      e = convert_b(src, src_ld, !h->b_row_major, h->d_B, ldk, n, h->cols, h->sopt.precision,
+                    h->stream, /*keep_fp32=*/h->sopt.precision == PREC_TF32);
+  } else {
+    e = convert_b(src, src_ld, h->b_row_major, h->d_B, ldk, h->cols, n, h->sopt.precision, h->stream, false);
+  }
+  dev_free(d_stage, h->stream);
   if (e != cudaSuccess) return fail_cuda(e, "B conversion");
 
   if (n != h->n) {
-    const char* serr = build_assignment(h->st, h->sopt, n, h->cols, &h->as);
-    if (*serr) return fail(SPARTA_ERR_INVALID, serr);
-    cudaFree(h->d_items); cudaFree(h->d_cta_ptr); cudaFree(h->d_cta_items);
-    h->d_items = nullptr; h->d_cta_ptr = nullptr; h->d_cta_items = nullptr;
-    CU_TRY(upload_vec(h->as.items, &h->d_items, h->stream));
-    CU_TRY(upload_vec(h->as.cta_ptr, &h->d_cta_ptr, h->stream));
-    CU_TRY(upload_vec(h->as.cta_items, &h->d_cta_items, h->stream));
+    if (h->kind == 0) {
+      const char* serr = build_assignment(h->st, h->sopt, n, h->cols, &h->as);
+      if (*serr) return fail(SPARTA_ERR_INVALID, serr);
+      dev_free(h->d_items, h->stream); dev_free(h->d_cta_ptr, h->stream); dev_free(h->d_cta_items, h->stream);
+      CU_TRY(upload_vec(h->as.items, &h->d_items, h->stream));
+      CU_TRY(upload_vec(h->as.cta_ptr, &h->d_cta_ptr, h->stream));
+      CU_TRY(upload_vec(h->as.cta_items, &h->d_cta_items, h->stream));
+    }
     // C: column-major ld padded to 4 rows so the epilogue can use 16-byte stores
-    h->ldc = h->c_row_major ? n : (h->st.rows + 3) / 4 * 4;
-    const size_t c_elems = h->c_row_major ? static_cast<size_t>(h->st.rows) * n : static_cast<size_t>(h->ldc) * n;
+    h->ldc = h->c_row_major ? n : (h->rows + 3) / 4 * 4;
+    const size_t c_elems = h->c_row_major ? static_cast<size_t>(h->rows) * n : static_cast<size_t>(h->ldc) * n;
     const size_t c_bytes = std::max<size_t>(c_elems, 4) * sizeof(float);
     if (c_bytes > h->c_cap) {
-      cudaFree(h->d_C);
-      h->d_C = nullptr; h->c_cap = 0;
-      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_C), c_bytes));
+      dev_free(h->d_C, h->stream);
+      h->c_cap = 0;
+      CU_TRY(dev_alloc(&h->d_C, c_bytes, h->stream));
       h->c_cap = c_bytes;
     }
     CU_TRY(cudaMemsetAsync(h->d_C, 0, c_bytes, h->stream));
     h->n = n;
   }
-  CU_TRY(cudaEventRecord(t1, h->stream));
-  CU_TRY(cudaEventSynchronize(t1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, t0, t1);
-  h->upload_ms = ms;
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
+  CU_TRY(cudaEventRecord(h->up1, h->stream));
+  if (!defer_sync) CU_TRY(cudaStreamSynchronize(h->stream));
   return SPARTA_OK;
+}
+
+int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device) {
+  return set_b_impl(h, B, ld, n, on_device, false);
 }
 
 static int copy_c(sparta_handle* h, float* C, int64_t ld, int on_device, bool to_handle) {
   if (!h || !C) return fail(SPARTA_ERR_INVALID, "NULL handle or C");
   if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called first");
-  const int64_t rows = h->st.rows;
+  const int64_t rows = h->rows;
   const int64_t lines = h->c_row_major ? rows : h->n;
   const int64_t width = h->c_row_major ? h->n : rows;
   if (ld < width) return fail(SPARTA_ERR_INVALID, "leading dimension of C too small");
@@ -460,6 +640,24 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");
   if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called before run");
   CU_TRY(cudaSetDevice(h->device));
+  if (h->kind == 1) {
+    if (trace) return fail(SPARTA_ERR_INVALID, "CSR handles have no worker timeline");
+    CsrParams c;
+    memset(&c, 0, sizeof(c));
+    c.rowptr = h->d_rowptr; c.colind = h->d_colind; c.val = h->d_val; c.row_order = h->d_row_order;
+    c.B = h->d_B; c.C = h->d_C;
+    c.c_sr = h->c_row_major ? h->ldc : 1;
+    c.c_sj = h->c_row_major ? 1 : h->ldc;
+    c.rows = h->rows;
+    c.heavy_rows = h->heavy_rows;
+    c.n = static_cast<int32_t>(h->n);
+    c.ldn = static_cast<int32_t>(h->ldk);
+    c.accumulate = h->accumulate;
+    const cudaError_t e = spmm_csr_launch(c, h->sopt.precision, h->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "CSR kernel launch");
+    if (h->rows > 0) ++h->launches;
+    return SPARTA_OK;
+  }
   if (h->as.grid == 0) return SPARTA_OK;  // empty shard: nothing to compute
   SpmmParams p;
   memset(&p, 0, sizeof(p));
@@ -478,8 +676,10 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   p.kind_tf32 = h->sopt.precision == PREC_TF32;
   p.panel_stages = h->panel_stages;
   p.a_ring_bytes = h->a_ring_bytes;
-  p.acc_stages = 512 / h->sopt.acc_cols;
-  p.acc_stage_cols = h->sopt.acc_cols;
+  // bounded chains: 256 working columns + 256 master columns, one accumulator stage
+  p.master_col = h->st.master_col;
+  p.acc_stages = h->st.master_col > 0 ? 1 : 512 / h->st.acc_cols;
+  p.acc_stage_cols = h->st.acc_cols;
   const char* err = "";
   cudaError_t e = spmm_launch(p, h->d_B, h->cols, h->ldk, h->sopt.precision, h->as.grid, h->stream, &err);
   if (e != cudaSuccess) return fail_cuda(e, err);
@@ -496,14 +696,14 @@ int sparta_run_traced(sparta_handle* h, int32_t worker, uint64_t* records, int64
   CU_TRY(cudaSetDevice(h->device));
   const size_t bytes = static_cast<size_t>(capacity) * 4 * 2 * 2 * sizeof(uint64_t);
   unsigned long long* d = nullptr;
-  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&d), bytes));
+  CU_TRY(dev_alloc(&d, bytes, h->stream));
   cudaError_t e = cudaMemsetAsync(d, 0, bytes, h->stream);
   int rc = SPARTA_OK;
   if (e == cudaSuccess) rc = launch(h, d, worker, static_cast<int>(capacity));
   if (e == cudaSuccess && rc == SPARTA_OK)
     e = cudaMemcpyAsync(records, d, bytes, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && rc == SPARTA_OK) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d);
+  dev_free(d, h->stream);
   if (rc) return rc;
   if (e != cudaSuccess) return fail_cuda(e, "traced run");
   return SPARTA_OK;
@@ -556,9 +756,22 @@ static void fill_stats(const Structure& st, const Assignment& as, int64_t cols, 
 int sparta_get_stats(sparta_handle* h, sparta_stats* out) {
   if (!h || !out) return fail(SPARTA_ERR_INVALID, "NULL handle or stats");
   fill_stats(h->st, h->as, h->cols, h->block_rows, h->panel_stages, h->a_ring_bytes, out);
-  out->b_bytes = static_cast<int64_t>(h->n) * h->ldk * prec_esize(h->sopt.precision);
-  out->c_bytes = h->c_row_major ? h->st.rows * h->n * 4 : h->ldc * h->n * 4;
-  out->upload_ms = h->upload_ms;
+  if (h->kind == 1) {
+    out->rows = h->rows;
+    out->nztot = h->nnz;
+    out->smem_bytes = 0;
+    out->grid = static_cast<int32_t>(std::min<int64_t>((h->rows + 7) / 8, INT32_MAX));
+    out->b_bytes = h->cols * h->ldk * (h->sopt.precision == PREC_TF32 ? 4 : 2);
+  } else {
+    out->b_bytes = static_cast<int64_t>(h->n) * h->ldk * prec_esize(h->sopt.precision);
+  }
+  out->c_bytes = h->c_row_major ? h->rows * h->n * 4 : h->ldc * h->n * 4;
+  float up = 0;
+  if (cudaSetDevice(h->device) == cudaSuccess && cudaEventSynchronize(h->up1) == cudaSuccess &&
+      cudaEventElapsedTime(&up, h->up0, h->up1) == cudaSuccess)
+    out->upload_ms = up;
+  else
+    cudaGetLastError();
   out->kernel_launches = h->launches;
   return SPARTA_OK;
 }
@@ -568,6 +781,48 @@ int sparta_destroy(sparta_handle* h) {
   return SPARTA_OK;
 }
 
+// One-shot data flow shared by the three formats: nothing synchronises between the upload of A,
+// the upload of B, the kernel and the download of C -- they are one in-order sequence on the
+// handle's stream, and the host scheduler overlaps the A upload (create_common).
+}  // extern "C"
+template <class CreateFn>
+static int one_shot(const char* name, CreateFn create, const float* B, int64_t ldb, int64_t n, float* C,
+                    int64_t ldc, float* dt_ms) {
+  sparta_handle* h = nullptr;
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;   // phase breakdown of the call on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
+  int rc = create(&h);
+  if (rc) return rc;
+  const auto t1 = now();
+  rc = set_b_impl(h, B, ldb, n, 0, true);
+  const auto t2 = now();
+  if (!rc) {
+    cudaError_t e = cudaEventRecord(h->ev0, h->stream);
+    if (e == cudaSuccess) { rc = sparta_run_async(h); e = cudaEventRecord(h->ev1, h->stream); }
+    if (e != cudaSuccess) rc = fail_cuda(e, "event record");
+  }
+  const auto t3 = now();
+  if (!rc) rc = sparta_get_C(h, C, ldc, 0);   // synchronises the stream
+  const auto t4 = now();
+  if (!rc && dt_ms) {
+    cudaError_t e = cudaEventElapsedTime(dt_ms, h->ev0, h->ev1);
+    if (e != cudaSuccess) rc = fail_cuda(e, "cudaEventElapsedTime");
+  }
+  if (rc) cudaStreamSynchronize(h->stream);   // host buffers must be idle before we return
+  const std::string keep = g_last_error;
+  sparta_destroy(h);
+  if (timing)
+    fprintf(stderr, "%s: enqueue create %.1f ms (host schedule overlapped with the A upload), set_B %.1f, run %.1f, "
+            "wait + get_C %.1f, destroy %.1f\n", name, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
+  if (rc) g_last_error = keep;
+  return rc;
+}
+extern "C" {
+
 int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
                     const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
                     const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
@@ -576,29 +831,9 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
   memset(&o, 0, sizeof(o));
   o.struct_size = sizeof(o);
   o.precision = precision;
-  sparta_handle* h = nullptr;
-  const bool timing = getenv("SPARTA_TIMING") != nullptr;   // phase breakdown of the one-shot call on stderr
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-    return std::chrono::duration<double, std::milli>(b - a).count();
-  };
-  const auto t0 = now();
-  int rc = sparta_vbr_create(&h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o);
-  if (rc) return rc;
-  const auto t1 = now();
-  rc = sparta_set_B(h, B, ldb, n, 0);
-  const auto t2 = now();
-  if (!rc) rc = sparta_run(h, dt_ms);
-  const auto t3 = now();
-  if (!rc) rc = sparta_get_C(h, C, ldc, 0);
-  const auto t4 = now();
-  const std::string keep = g_last_error;
-  sparta_destroy(h);
-  if (timing)
-    fprintf(stderr, "sparta_vbr_spmm: create %.1f ms (schedule + A upload + repack), set_B %.1f, run %.1f, get_C %.1f, destroy %.1f\n",
-            ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
-  if (rc) g_last_error = keep;
-  return rc;
+  return one_shot("sparta_vbr_spmm", [&](sparta_handle** h) {
+    return vbr_create_impl(h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o, true);
+  }, B, ldb, n, C, ldc, dt_ms);
 }
 
 int sparta_bellpack_spmm(int64_t rows, int64_t cols, int64_t ell_blocksize,
@@ -610,16 +845,41 @@ int sparta_bellpack_spmm(int64_t rows, int64_t cols, int64_t ell_blocksize,
   memset(&o, 0, sizeof(o));
   o.struct_size = sizeof(o);
   o.precision = precision;
-  sparta_handle* h = nullptr;
-  int rc = sparta_bellpack_create(&h, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd, ellValues, &o);
-  if (rc) return rc;
-  rc = sparta_set_B(h, B, ldb, n, 0);
-  if (!rc) rc = sparta_run(h, dt_ms);
-  if (!rc) rc = sparta_get_C(h, C, ldc, 0);
-  const std::string keep = g_last_error;
-  sparta_destroy(h);
-  if (rc) g_last_error = keep;
-  return rc;
+  return one_shot("sparta_bellpack_spmm", [&](sparta_handle** h) {
+    return bellpack_create_impl(h, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd,
+                                ellValues, &o, true);
+  }, B, ldb, n, C, ldc, dt_ms);
+}
+
+int sparta_csr_spmm(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
+                    const float* val, const float* B, int64_t ldb, int64_t n, float* C, int64_t ldc,
+                    int precision, float* dt_ms) {
+  sparta_options o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  o.precision = precision;
+  return one_shot("sparta_csr_spmm", [&](sparta_handle** h) {
+    return csr_create_impl(h, rows, cols, rowptr, colind, val, &o, true);
+  }, B, ldb, n, C, ldc, dt_ms);
+}
+
+int sparta_release_workspace(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return SPARTA_OK; }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < ndev && d < 64; ++d) {
+    bool ready;
+    { std::lock_guard<std::mutex> lock(g_pool_mutex); ready = g_pool_ready[d]; }
+    if (!ready) continue;
+    cudaMemPool_t pool;
+    if (cudaSetDevice(d) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, d) != cudaSuccess) continue;
+    cudaDeviceSynchronize();
+    cudaMemPoolTrimTo(pool, 0);
+  }
+  cudaSetDevice(cur);
+  cudaGetLastError();
+  return SPARTA_OK;
 }
 
 int sparta_partition_block_rows(int64_t block_rows, const int64_t* row_part,
@@ -748,6 +1008,7 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
   p->sopt.pair = o.cta_pair != 1;
   p->sopt.sort_rows = o.row_order != 1;
   p->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
+  p->sopt.max_chain = o.max_chain;
   p->cols = cols; p->block_rows = br.count(); p->n = n;
   p->panel_stages = o.panel_stages;
   p->a_ring_bytes = ring_bytes_for(o.panel_stages);

@@ -14,6 +14,8 @@
 
 namespace sparta {
 
+constexpr int kPrecRawFp32 = 3;   // convert_b only: copy fp32 unchanged (the CSR kernel's fp32 mode)
+
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -71,7 +73,9 @@ __global__ void convert_b_colmajor_kernel(const float* __restrict__ src, int64_t
   for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < k_total;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float x = s[k];
-    if (precision == PREC_TF32)
+    if (precision == kPrecRawFp32)
+      reinterpret_cast<float*>(dst)[j * ldk + k] = x;
+    else if (precision == PREC_TF32)
       reinterpret_cast<uint32_t*>(dst)[j * ldk + k] = to_tf32(x);
     else if (precision == PREC_BF16)
       reinterpret_cast<__nv_bfloat16*>(dst)[j * ldk + k] = __float2bfloat16_rn(x);
@@ -96,7 +100,9 @@ __global__ void convert_b_rowmajor_kernel(const float* __restrict__ src, int64_t
     const int64_t j = j0 + i, k = k0 + threadIdx.x;
     if (j < n && k < k_total) {
       const float x = tile[threadIdx.x][i];
-      if (precision == PREC_TF32)
+      if (precision == kPrecRawFp32)
+        reinterpret_cast<float*>(dst)[j * ldk + k] = x;
+      else if (precision == PREC_TF32)
         reinterpret_cast<uint32_t*>(dst)[j * ldk + k] = to_tf32(x);
       else if (precision == PREC_BF16)
         reinterpret_cast<__nv_bfloat16*>(dst)[j * ldk + k] = __float2bfloat16_rn(x);
@@ -120,8 +126,10 @@ cudaError_t pack_a_images(const float* src_dev, const PackJob* jobs_dev, int64_t
 
 cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void* dst_dev,
                       int64_t ldk, int64_t k_total, int64_t n, int precision,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool keep_fp32) {
   if (k_total == 0 || n == 0) return cudaSuccess;
+  const size_t esz = keep_fp32 ? 4 : prec_esize(precision);
+  if (keep_fp32) precision = kPrecRawFp32;
   if (!row_major) {
     // gridDim.y <= 65535: loop over column slabs
     for (int64_t j0 = 0; j0 < n; j0 += 65535) {
@@ -129,7 +137,6 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
       int64_t gx = (k_total + 255) / 256;
       if (gx > 1024) gx = 1024;
       dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(nj));
-      const size_t esz = prec_esize(precision);
       convert_b_colmajor_kernel<<<grid, 256, 0, stream>>>(
           src_dev + j0 * ld_src, ld_src, static_cast<uint8_t*>(dst_dev) + j0 * ldk * esz, ldk,
           k_total, nj, precision);
@@ -138,7 +145,6 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
     for (int64_t j0 = 0; j0 < n; j0 += 32 * 65535LL) {
       const int64_t nj = (n - j0 < 32 * 65535LL) ? (n - j0) : 32 * 65535LL;
       dim3 grid(static_cast<unsigned>((k_total + 31) / 32), static_cast<unsigned>((nj + 31) / 32));
-      const size_t esz = prec_esize(precision);
       convert_b_rowmajor_kernel<<<grid, dim3(32, 8), 0, stream>>>(
           src_dev + j0, ld_src, static_cast<uint8_t*>(dst_dev) + j0 * ldk * esz, ldk, k_total, nj,
           precision);

@@ -10,6 +10,6 @@ cudaError_t pack_a_images(const float* src_dev, const PackJob* jobs_dev, int64_t
 
 cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void* dst_dev,
                       int64_t ldk, int64_t k_total, int64_t n, int precision,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool keep_fp32 = false);
 
 }  // namespace sparta

@@ -51,9 +51,21 @@ struct Chunk {
 constexpr int kTableWords = 4 + 2 * 32;
 constexpr int kTableBytes = kTableWords * 4;   // 272: the largest table (32 runs)
 
+// A work item = one PASS of a (super-row, column tile): a contiguous range of the super-row's
+// chunks accumulated into the working accumulator.  Normally a super-row is one pass.  When the
+// accumulation chain is bounded (ScheduleOptions::max_chain, the tf32 default) a long super-row is
+// cut into several passes executed back to back by the same worker: the epilogue folds every
+// pass into a MASTER copy of the accumulator kept in the other half of TMEM with round-to-nearest
+// fp32 adds, and only the last pass writes C.  This bounds the error of the tensor core's
+// truncating fp32 accumulation, which otherwise grows linearly with the number of MMAs.
+constexpr uint32_t kItemNotFirst = 1u << 31;   // fold the master copy into this pass's result
+constexpr uint32_t kItemNotLast  = 1u << 30;   // store the result to the master copy, not to C
+constexpr uint32_t kItemCountMask = (1u << 30) - 1;
 struct Item {
   int32_t srow;       // super-row id
-  int32_t j0;         // first column of B/C of this 128-wide column tile
+  int32_t j0;         // first column of B/C of this column tile
+  int32_t chunk_off;  // first chunk of the pass, relative to SuperRow::chunk_begin
+  uint32_t count;     // chunks in the pass | kItemNotFirst | kItemNotLast
 };
 
 // One packed A image = h_pad rows x 128 bytes in the K-major SWIZZLE_128B

@@ -14,10 +14,34 @@ namespace sparta {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+static const char* build_structure_for(const BlockRows& br, const ScheduleOptions& opt, int64_t chain,
+                                       Structure* out);
+
+// chain limit in MMAs per accumulator: tf32 sums are held to <= 1e-5, and the tensor
+// core's fp32 accumulation truncates (measured: 5.6e-5 relative on an all-positive chain of ~8000
+// MMAs), so tf32 bounds the chain by default; bf16 / fp16 (tolerance 2e-2) do not.
 const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Structure* out) {
+  int64_t chain = opt.max_chain;
+  if (chain == 0) chain = opt.precision == PREC_TF32 ? 256 : -1;
+  if (chain > 0 && chain < 8) return "max_chain must be at least 8";
+  // First try the requested accumulator width with unbounded chains; only if some super-row
+  // exceeds the limit rebuild with 256-column super-rows (the other 256 TMEM columns then hold
+  // the master copy) cut into passes.
+  const char* e = build_structure_for(br, opt, -1, out);
+  if (*e || chain < 0 || out->max_chain_seen <= chain) return e;
+  ScheduleOptions o2 = opt;
+  o2.acc_cols = 256;
+  return build_structure_for(br, o2, chain, out);
+}
+
+static const char* build_structure_for(const BlockRows& br, const ScheduleOptions& opt, int64_t chain,
+                                       Structure* out) {
   Structure& st = *out;
   st = Structure();
   st.pair = opt.pair ? 1 : 0;
+  st.acc_cols = opt.acc_cols;
+  st.master_col = chain > 0 ? 256 : 0;
+  std::vector<int32_t> ksteps_of;   // per chunk of the current super-row
   if (br.w <= 0) return "column block size must be positive";
   if (opt.seg_rows < 16 || opt.seg_rows > 256 || opt.seg_rows % 16) return "seg_rows must be a multiple of 16 in [16,256]";
   if (opt.acc_cols != 256 && opt.acc_cols != 512) return "acc_cols must be 256 or 512";
@@ -198,10 +222,31 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
       i = i1;
     }
     sr.chunk_count = static_cast<int32_t>(st.chunks.size()) - sr.chunk_begin;
+    // passes: balanced cuts so that no pass issues more than `chain` MMAs into an accumulator
+    st.pass_ptr.push_back(static_cast<int32_t>(st.pass_off.size()));
+    {
+      int64_t total = 0;
+      for (int32_t c = 0; c < sr.chunk_count; ++c) total += st.chunks[sr.chunk_begin + c].ksteps;
+      const int64_t passes = chain > 0 ? std::max<int64_t>(1, (total + chain - 1) / chain) : 1;
+      const int64_t target = (total + passes - 1) / passes;
+      int64_t run = 0;
+      st.pass_off.push_back(0);
+      for (int32_t c = 0; c < sr.chunk_count; ++c) {
+        const int64_t k = st.chunks[sr.chunk_begin + c].ksteps;
+        if (run > 0 && run + k > target) {
+          st.max_chain_seen = std::max(st.max_chain_seen, run);
+          st.pass_off.push_back(c);
+          run = 0;
+        }
+        run += k;
+      }
+      st.max_chain_seen = std::max(st.max_chain_seen, run);
+    }
     st.srows.push_back(sr);
     st.srow_cost.push_back(cost);
     s0 = s1;
   }
+  st.pass_ptr.push_back(static_cast<int32_t>(st.pass_off.size()));
   if (st.chunks.size() > static_cast<size_t>(INT32_MAX)) return "too many chunks";
   return "";
 }
@@ -223,10 +268,10 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
   if (n <= 0 || n > INT32_MAX - tile) return "invalid number of B columns";
   const int64_t tiles = (n + tile - 1) / tile;
   const int64_t n_srows = static_cast<int64_t>(st.srows.size());
-  const int64_t n_items = n_srows * tiles;
+  const int64_t n_items = static_cast<int64_t>(st.pass_off.size()) * tiles;   // one item per pass
   if (n_items > INT32_MAX) return "too many work items";
   int workers = std::max(1, opt.num_ctas / (st.pair ? 2 : 1));
-  workers = static_cast<int>(std::min<int64_t>(workers, std::max<int64_t>(n_items, 1)));
+  workers = static_cast<int>(std::min<int64_t>(workers, std::max<int64_t>(n_srows * tiles, 1)));
   as.workers = n_items ? workers : 0;
   as.grid = as.workers * (st.pair ? 2 : 1);
   as.cta_ptr.assign(as.workers + 1, 0);
@@ -264,9 +309,18 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
     for (int32_t s : by_cost) {
       Load l = heap.top();
       heap.pop();
+      const int32_t p0 = st.pass_ptr[s], p1 = st.pass_ptr[s + 1];
+      const int32_t n_chunks = st.srows[s].chunk_count;
       for (int m = 0; m < in_group; ++m) {
-        per_worker[l.second * team + m].push_back(static_cast<int32_t>(as.items.size()));
-        as.items.push_back(Item{s, static_cast<int32_t>((t0 + m) * tile)});
+        for (int32_t ps = p0; ps < p1; ++ps) {   // the passes of one (super-row, tile) stay together
+          const int32_t off = st.pass_off[ps];
+          const int32_t end = ps + 1 < p1 ? st.pass_off[ps + 1] : n_chunks;
+          uint32_t count = static_cast<uint32_t>(end - off);
+          if (ps > p0) count |= kItemNotFirst;
+          if (ps + 1 < p1) count |= kItemNotLast;
+          per_worker[l.second * team + m].push_back(static_cast<int32_t>(as.items.size()));
+          as.items.push_back(Item{s, static_cast<int32_t>((t0 + m) * tile), off, count});
+        }
       }
       l.first += st.srow_cost[s];
       heap.push(l);

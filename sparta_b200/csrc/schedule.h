@@ -29,6 +29,7 @@ struct ScheduleOptions {
   int pair = 1;            // 1: two CTAs (one TPC) share a super-row through tcgen05 cta_group::2
   int sort_rows = 1;       // 1: group block-rows of similar nonzero-block count into super-rows
   int64_t l2_slab_bytes = 64ll << 20;  // B columns kept L2-resident at a time (see build_assignment)
+  int max_chain = 0;       // longest accumulation chain in tcgen05.mma instructions (0: default, -1: unlimited)
 };
 
 struct Structure {           // independent of the number of B columns
@@ -38,6 +39,11 @@ struct Structure {           // independent of the number of B columns
   std::vector<PackJob>  jobs;
   std::vector<uint32_t> tables;      // run tables of all chunks, back to back (see sched_types.h)
   std::vector<double>   srow_cost;   // modelled tensor cycles per column tile
+  std::vector<int32_t>  pass_ptr;    // [srows + 1] ranges into pass_off
+  std::vector<int32_t>  pass_off;    // per pass: first chunk (relative to the super-row), see Item
+  int master_col = 0;                // > 0: TMEM column of the master accumulators (bounded chains)
+  int acc_cols = 512;                // accumulator columns the super-rows were packed for
+  int64_t max_chain_seen = 0;        // longest accumulation chain (MMAs) of any pass
   uint64_t a_bytes = 0;              // bytes of packed A images
   int64_t  nztot = 0;                // sum over blocks of h*w (the reference's VBR::nztot)
   int64_t  n_blocks = 0;

@@ -215,6 +215,14 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       "r"(z)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -249,6 +257,13 @@ __device__ __forceinline__ void trace_put(const SpmmParams& p, bool on, int zone
   }
 }
 
+
+__device__ __forceinline__ Item load_item(const SpmmParams& p, int it) {
+  const int4 raw = __ldg(reinterpret_cast<const int4*>(p.items) + p.cta_items[it]);
+  Item item;
+  item.srow = raw.x; item.j0 = raw.y; item.chunk_off = raw.z; item.count = static_cast<uint32_t>(raw.w);
+  return item;
+}
 
 // ------------------------------------------------------------------ kernel
 // kPair = false: one CTA owns a (super-row, 128-column tile) item; MMAs are cta_group::1, M = 128.
@@ -344,26 +359,27 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       if (++rel_slot == static_cast<uint32_t>(P)) { rel_slot = 0; rel_phase ^= 1u; }
     };
     for (int it = it_begin; it < it_end; ++it) {
-      const Item item = p.items[p.cta_items[it]];
+      const Item item = load_item(p, it);
       const SuperRow sr = p.srows[item.srow];
       const int j0 = item.j0 + static_cast<int>(rank) * kTileJ;
-      const int4* recs = reinterpret_cast<const int4*>(p.chunks + sr.chunk_begin);
+      const int4* recs = reinterpret_cast<const int4*>(p.chunks + sr.chunk_begin + item.chunk_off);
+      const int chunk_count = static_cast<int>(item.count & kItemCountMask);   // chunks of this pass
       int4 nxt = make_int4(0, 0, 0, 0);
       int2 nxt_t = make_int2(0, 0);
-      if (lane < sr.chunk_count) {
+      if (lane < chunk_count) {
         nxt = __ldg(recs + 2 * lane);
         const int4 hi = __ldg(recs + 2 * lane + 1);
         nxt_t = make_int2(hi.y, hi.z);             // tbl_bytes, tbl_off16
       }
-      for (int c0 = 0; c0 < sr.chunk_count; c0 += 32) {
+      for (int c0 = 0; c0 < chunk_count; c0 += 32) {
         const int4 cur = nxt;
         const int2 cur_t = nxt_t;
-        if (c0 + 32 + lane < sr.chunk_count) {
+        if (c0 + 32 + lane < chunk_count) {
           nxt = __ldg(recs + 2 * (c0 + 32 + lane));
           const int4 hi = __ldg(recs + 2 * (c0 + 32 + lane) + 1);
           nxt_t = make_int2(hi.y, hi.z);
         }
-        const int batch = min(32, sr.chunk_count - c0);
+        const int batch = min(32, chunk_count - c0);
         for (int i = 0; i < batch; ++i) {
           const int ch_k0 = __shfl_sync(0xFFFFFFFFu, cur.x, i);
           const uint32_t ch_off16 = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.z, i));
@@ -419,7 +435,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       const uint32_t remote = map_to_cta(bar_full, 0);
       uint32_t slot = 0, phase = 0;
       for (int it = it_begin; it < it_end; ++it) {
-        const int chunk_count = p.srows[p.items[p.cta_items[it]].srow].chunk_count;
+        const int chunk_count = static_cast<int>(load_item(p, it).count & kItemCountMask);
         for (int c = 0; c < chunk_count; ++c) {
           mbar_wait(bar_full + 8 * slot, phase, 6);
           if (lane == 0) mbar_arrive_remote_relaxed(remote + 8 * slot);
@@ -433,8 +449,8 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       uint32_t acc_use[2] = {0, 0};
       int local = 0;
       for (int it = it_begin; it < it_end; ++it, ++local) {
-        const Item item = p.items[p.cta_items[it]];
-        const int chunk_count = p.srows[item.srow].chunk_count;
+        const Item item = load_item(p, it);
+        const int chunk_count = static_cast<int>(item.count & kItemCountMask);
         const int as = (p.acc_stages == 2) ? (local & 1) : 0;
         const unsigned long long ta0 = tr ? sm_clock() : 0ull;
         mbar_wait(bar_acc_empty + 8 * as, acc_use[as] & 1, 3);
@@ -518,9 +534,13 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
     int local = 0;
     const bool c_aligned = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
     for (int it = it_begin; it < it_end; ++it, ++local) {
-      const Item item = p.items[p.cta_items[it]];
+      const Item item = load_item(p, it);
       const SuperRow sr = p.srows[item.srow];
       const int as = (p.acc_stages == 2) ? (local & 1) : 0;
+      // bounded accumulation chains: passes other than the last fold their result into the master
+      // copy of the accumulator (TMEM columns master_col..) instead of writing C
+      const bool fold_in = (item.count & kItemNotFirst) != 0;
+      const bool to_master = (item.count & kItemNotLast) != 0;
       mbar_wait(bar_acc_full + 8 * as, acc_use[as] & 1, 5);
       const unsigned long long te0 = (tr && warp == 2 && lane == 0) ? sm_clock() : 0ull;
       ++acc_use[as];
@@ -535,8 +555,21 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
         for (int c0 = 0; c0 < sg.h_pad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(t_acc + sg.tmem_col + c0, v);
-          tmem_wait_ld();
+          if (fold_in) {
+            uint32_t m[16];
+            tmem_ld16(t_acc + p.master_col + sg.tmem_col + c0, m);
+            tmem_wait_ld();
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              v[r] = __float_as_uint(__fadd_rn(__uint_as_float(v[r]), __uint_as_float(m[r])));
+          } else {
+            tmem_wait_ld();
+          }
           tmem_st16_zero(t_acc + sg.tmem_col + c0);
+          if (to_master) {
+            tmem_st16(t_acc + p.master_col + sg.tmem_col + c0, v);
+            continue;
+          }
           if (jv) {
             float* dst = cj + static_cast<int64_t>(sg.c_row0 + c0) * p.c_sr;
             if (vec_ok && c0 + 16 <= sg.h) {

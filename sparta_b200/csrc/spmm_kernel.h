@@ -25,6 +25,7 @@ struct SpmmParams {
   int32_t         a_ring_bytes; // bytes of the A-image ring (multiple of 1024)
   int32_t         acc_stages;   // 1 or 2 TMEM accumulator stages
   int32_t         acc_stage_cols; // 512 / acc_stages
+  int32_t         master_col;   // > 0: TMEM column offset of the master accumulators (bounded chains)
   int32_t         pair;         // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2); cta_ptr is per pair
   // optional timeline of one worker (sparta_run_traced): 4 zones x 2 ranks x trace_cap records of
   // {t0, t1} SM clocks; zone 0 producer per chunk, 1 MMA per chunk, 2 epilogue per item,

@@ -28,7 +28,7 @@ class Options(C.Structure):
         ("seg_rows", C.c_int32), ("acc_cols", C.c_int32), ("panel_stages", C.c_int32),
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
         ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("max_chain", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -60,6 +60,8 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, C.POINTER(Options)]),
     "sparta_bellpack_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, _vp, _vp, C.POINTER(Options)]),
+    "sparta_csr_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, _vp, _vp, _vp,
+                                    C.POINTER(Options)]),
     "sparta_set_B": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int]),
     "sparta_set_C": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
     "sparta_run": (C.c_int, [_vp, C.POINTER(C.c_float)]),
@@ -78,6 +80,9 @@ SIGNATURES = {
     "sparta_bellpack_spmm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp,
                                        _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
                                        C.POINTER(C.c_float)]),
+    "sparta_csr_spmm": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp,
+                                  C.c_int64, C.c_int, C.POINTER(C.c_float)]),
+    "sparta_release_workspace": (C.c_int, []),
     "sparta_partition_block_rows": (C.c_int, [C.c_int64, _vp, _vp, C.c_int32, _vp]),
     "sparta_host_blocking": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
                                        C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -190,6 +195,18 @@ class Handle:
                                           _ptr(ind), _ptr(vals), C.byref(o)))
         return cls(h, None)
 
+    @classmethod
+    def from_csr(cls, rows, cols, rowptr, colind, val=None, **opts):
+        """Flat CSR (val=None: pattern-only, all ones).  block_row_begin/end select ROWS here."""
+        lib = load()
+        rowptr, colind = _i64(rowptr), _i64(colind)
+        val = None if val is None else _f32(val)
+        o = make_options(**opts)
+        h = _vp()
+        _check(lib.sparta_csr_create(C.byref(h), rows, cols, _ptr(rowptr), _ptr(colind),
+                                     None if val is None else _ptr(val), C.byref(o)))
+        return cls(h, None)
+
     def set_B(self, B, ld, n):
         """B: numpy fp32 array (host) in the handle's B layout."""
         B = _f32(B)
@@ -262,7 +279,8 @@ SROW_DT = np.dtype([("seg_begin", "<i4"), ("seg_count", "<i4"), ("chunk_begin", 
 CHUNK_DT = np.dtype([("k0", "<i4"), ("mask", "<u4"), ("a_off16", "<u4"), ("a_bytes", "<u4"),
                      ("ksteps", "<i4"), ("tbl_bytes", "<u4"), ("tbl_off16", "<u4"),
                      ("pad", "<i4")])
-ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4")])
+ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4"), ("chunk_off", "<i4"), ("count", "<u4")])
+ITEM_NOT_FIRST, ITEM_NOT_LAST, ITEM_COUNT_MASK = 1 << 31, 1 << 30, (1 << 30) - 1
 JOB_DT = np.dtype([("src_base", "<i8"), ("src_rs", "<i8"), ("src_ks", "<i8"), ("h", "<i4"),
                    ("h_pad", "<i4"), ("k_lo", "<i4"), ("k_w", "<i4"), ("dst_off16", "<u4"),
                    ("pad", "<i4", (3,))])

@@ -62,7 +62,10 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
     Cm = np.full((n, rows), np.nan, dtype=np.float32)
     visited = np.zeros(len(items), dtype=bool)
     assert len(plan["cta_ptr"]) - 1 == plan["stats"]["grid"] // nshare
+    NOT_FIRST, NOT_LAST, COUNT = 1 << 31, 1 << 30, (1 << 30) - 1
     for worker in range(len(plan["cta_ptr"]) - 1):
+        master = {}        # per pair rank: the master accumulators of the (super-row, tile) in flight
+        open_pass = None   # (srow, j0, next chunk) while a multi-pass item is in flight
         for it in plan["cta_items"][plan["cta_ptr"][worker]:plan["cta_ptr"][worker + 1]]:
             assert not visited[it]
             visited[it] = True
@@ -70,11 +73,23 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
             sr = srows[item["srow"]]
             sg_all = segs[sr["seg_begin"]:sr["seg_begin"] + sr["seg_count"]]
             tcols = [int(c) for c in sg_all["tmem_col"]] + [int(sr["n_cols"])]
+            cnt, off = int(item["count"]) & COUNT, int(item["chunk_off"])
+            fold_in, to_master = bool(int(item["count"]) & NOT_FIRST), bool(int(item["count"]) & NOT_LAST)
+            # passes of one (super-row, tile) run back to back on one worker, in chunk order
+            if fold_in:
+                assert open_pass == (int(item["srow"]), int(item["j0"]), off)
+            else:
+                assert open_pass is None and off == 0
+            open_pass = (int(item["srow"]), int(item["j0"]), off + cnt) if to_master else None
+            if not to_master:
+                assert off + cnt == int(sr["chunk_count"])
+            if fold_in or to_master:   # working + master accumulators must both fit in TMEM
+                assert int(sr["n_cols"]) <= 256
             for cta in range(nshare):      # each CTA of a pair owns 128 of the item's columns
                 j0 = int(item["j0"]) + cta * 128
                 jj = max(0, min(128, n - j0))
                 acc = np.zeros((128, int(sr["n_cols"])), dtype=np.float32)
-                for ch in chunks[sr["chunk_begin"]:sr["chunk_begin"] + sr["chunk_count"]]:
+                for ch in chunks[sr["chunk_begin"] + off:sr["chunk_begin"] + off + cnt]:
                     panel = np.zeros((128, katom), dtype=np.float32)  # TMA box, zero fill out of bounds
                     k0 = int(ch["k0"])
                     assert (k0 * esize) % 16 == 0, "TMA needs a 16-byte aligned k coordinate"
@@ -106,8 +121,14 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
                         acc[:, col:col + N] += panel[:, :kuse] @ img[:, :kuse].T
                         used += N * 128
                     assert used == int(ch["a_bytes"])
+                if fold_in:
+                    acc = acc + master[cta]
+                if to_master:
+                    master[cta] = acc
+                    continue
                 for sg in sg_all:
                     Cm[j0:j0 + jj, sg["c_row0"]:sg["c_row0"] + sg["h"]] = \
                         acc[:jj, sg["tmem_col"]:sg["tmem_col"] + sg["h"]]
+        assert open_pass is None
     assert visited.all()
     return Cm

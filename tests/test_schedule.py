@@ -82,3 +82,44 @@ def test_plan_shard_range(lib, oracle):
         mab_lo = int(sum(v["nzcount"][b] * 32 * 32 for b in range(lo)))
         pieces.append(sched_interp.run_plan(plan, v["mab"][mab_lo:], Bm, 256, n, rows_i))
     assert np.array_equal(np.concatenate(pieces, axis=1), Cref)
+
+
+@pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
+@pytest.mark.parametrize("precision,esize,max_chain", [("tf32", 4, 8), ("tf32", 4, 24), ("bf16", 2, 16), ("tf32", 4, 0)])
+def test_bounded_accumulation_chains(oracle, lib, precision, esize, max_chain, pair):
+    """max_chain cuts long super-rows into passes folded through the master accumulators; the
+    interpreter checks pass order, the 256-column limit and that the product is unchanged."""
+    rng = np.random.default_rng(21)
+    heights = [64, 30, 64, 64, 7, 64, 64, 64, 16, 64]
+    v = random_vbr(rng, len(heights), 2048, 64, heights, 0.6, values="int")
+    n = 200
+    Bm = rng.integers(-3, 4, size=(n, 2048)).astype(np.float32)
+    plan = sparta_b200.vbr_plan(v["rows"], 2048, 64, v["row_part"], v["nzcount"], v["jab"], n,
+                                precision=precision, cta_pair=pair, max_chain=max_chain)
+    items, srows, chunks = plan["items"], plan["srows"], plan["chunks"]
+    count = items["count"] & sparta_b200.lib.ITEM_COUNT_MASK
+    limit = max_chain if max_chain else 256          # the tf32 default
+    multi = (items["count"] & (sparta_b200.lib.ITEM_NOT_FIRST | sparta_b200.lib.ITEM_NOT_LAST)) != 0
+    if max_chain:
+        assert multi.any(), "the case is meant to need several passes"
+        assert np.all(srows["n_cols"] <= 256)
+    else:
+        assert not multi.any()                       # 32 blocks x 8 MMAs = 256: fits the default
+    for it in items:
+        c0 = srows[it["srow"]]["chunk_begin"] + it["chunk_off"]
+        n_mma = int(chunks["ksteps"][c0:c0 + (int(it["count"]) & sparta_b200.lib.ITEM_COUNT_MASK)].sum())
+        assert n_mma <= limit
+    assert count.sum() == sum(int(sr["chunk_count"]) for sr in srows) * len(np.unique(items["j0"]))
+    Cm = sched_interp.run_plan(plan, v["mab"], Bm, 2048, n, v["rows"], esize=esize)
+    assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
+
+
+def test_unbounded_chain_keeps_wide_super_rows(lib):
+    rng = np.random.default_rng(22)
+    v = random_vbr(rng, 16, 4096, 64, [64] * 16, 0.9, values="int")
+    a = sparta_b200.vbr_plan(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], 256, precision="bf16")
+    b = sparta_b200.vbr_plan(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], 256, precision="tf32",
+                             max_chain=-1)
+    c = sparta_b200.vbr_plan(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], 256, precision="tf32")
+    assert a["srows"]["n_cols"].max() == 512 and b["srows"]["n_cols"].max() == 512
+    assert c["srows"]["n_cols"].max() == 256 and len(c["items"]) > len(c["srows"])

@@ -266,3 +266,34 @@ def test_config2_shape_er_bellpack_blocking(lib):
                       "rows": 128})  # first two block-rows
     ref = (A @ B1.T.astype(np.float64)).T
     assert np.array_equal(outs[0][:, :128], ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("mode", ["single", "pair"])
+@pytest.mark.parametrize("precision,max_chain", [("tf32", 8), ("tf32", 40), ("bf16", 16), ("fp16", 100)])
+def test_bounded_chains_bit_exact(oracle, lib, precision, max_chain, mode):
+    """max_chain cuts super-rows into passes folded through the master accumulators in TMEM
+    (sched_types.h Item); integer operands must still be exact, whatever the cut."""
+    rng = np.random.default_rng(31)
+    heights = [64, 30, 64, 64, 7, 64, 64, 64, 16, 64, 1, 64]
+    v = random_vbr(rng, len(heights), 2048, 64, heights, 0.6, values="int")
+    n = 300
+    Bm = rng.integers(-3, 4, size=(n, 2048)).astype(np.float32)
+    Cg = gpu_multiply(v, Bm, n, precision, max_chain=max_chain, **MODES[mode])
+    assert np.array_equal(Cg, oracle.vbr_multiply(v, Bm, n))
+
+
+def test_tf32_long_positive_sums_within_1e5(lib):
+    """The tensor core's fp32 accumulation truncates, so an all-positive sum of thousands of MMAs
+    drifts (5.6e-5 measured at BASELINE config #3).  The tf32 default bounds the chain; the result
+    must stay within 1e-5 of fp64 on the tf32-rounded operands even for 512 blocks per row."""
+    rng = np.random.default_rng(32)
+    block_rows, cols, w, n = 8, 32768, 64, 128
+    v = random_vbr(rng, block_rows, cols, w, [64] * block_rows, 1.0, values="ones")
+    Bm = rng.random((n, cols), dtype=np.float32)
+    ref = round_to(Bm, "tf32").astype(np.float64) @ vbr_to_dense(v).T       # [n, rows]
+    Cg = gpu_multiply(v, Bm, n, "tf32")
+    assert rel_err(Cg, ref) <= TOL_ROUNDED
+    # the unbounded chain is what the limit protects against: it must not be MORE accurate
+    Cu = gpu_multiply(v, Bm, n, "tf32", max_chain=-1)
+    assert rel_err(Cu, ref) >= rel_err(Cg, ref)
+    assert rel_err(Cu, ref) <= TOL_UNROUNDED["tf32"]
