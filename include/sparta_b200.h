@@ -63,7 +63,11 @@ typedef struct sparta_options {
   int32_t max_chain;     /* longest run of tcgen05.mma accumulations into one TMEM accumulator before the
                             partial sum is drained and added to C in fp32 by the epilogue; 0 = the
                             precision's default (tf32: 128, bf16/fp16: unlimited), -1 = unlimited */
-  int32_t reserved[4];
+  int32_t split_k;       /* few super-rows per worker (small shards): cut the block-rows' column-block
+                            lists into equal-cost pieces, one per worker, partial sums added to C with
+                            fp32 reductions.  0: when the cost model says it pays (default), 1: never,
+                            2: always */
+  int32_t reserved[3];
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */
@@ -84,6 +88,9 @@ typedef struct sparta_stats {
   int64_t kernel_launches; /* sm_100a SpMM launches issued through this handle */
   int32_t team;            /* workers walking one super-row side by side (column tiles per L2 pass) */
   int32_t cta_pair;        /* 1 when the handle runs CTA pairs */
+  int32_t split_pieces;    /* (piece, column tile) items that add partial sums to C (split_k) */
+  int32_t zero_tiles;      /* C tiles zeroed before each launch for those pieces */
+  double  sched_max_cycles; /* modelled SM cycles of the worker that finishes last */
 } sparta_stats;
 
 const char* sparta_last_error(void);
@@ -101,6 +108,21 @@ int sparta_device_count(void);
 int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
                       int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                       const int64_t* jab, const float* mab, const sparta_options* opt);
+
+/* The INVERTED product C = B*A (-M 6 / -M 11): same VBR arrays, but B is n x rows and C is
+ * n x cols, both column-major with ld >= n (cuda_utilities.cpp:556-559,587-591), i.e. the handle
+ * computes C^T = A^T * B^T with the transposed blocks as the sparse operand: block-rows of the
+ * operand are A's column blocks, the contraction runs over A's rows in blocked order, block
+ * heights of any size become k extents.  set_B / get_C therefore take the ROW_MAJOR defaults
+ * ([rows][n] and [cols][n] with ld >= n).  The options' block_row_begin / block_row_end select a
+ * range of COLUMN BLOCKS (a slab of C's columns); the whole mab is uploaded for any range.
+ * Intended arithmetic of cublas_blockmat_multiplyBA (cuda_utilities.cpp:640-690), whose own
+ * indexing only works for constant heights and offsets B by block_col_size*ib (:645): see
+ * DESIGN.md.  Replaces the upload half of that routine and of cutlas_blockmat_multiplyBA
+ * (cutlass_bellpack_lib.cu:542-687). */
+int sparta_vbr_create_BA(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                         int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                         const int64_t* jab, const float* mab, const sparta_options* opt);
 
 /* A as the Blocked-ELL bundle produced by prepare_cusparse_BLOCKEDELLPACK
  * (cuda_utilities.cpp:1656-1710): ellColInd[ellColInd_rows*ellColInd_cols] with -1
@@ -167,6 +189,14 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
                     const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
                     const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
                     int64_t ldc, int precision, float* dt_ms);
+
+/* Replaces cublas_blockmat_multiplyBA (cuda_utilities.cpp:553-721, -M 6) and
+ * cutlas_blockmat_multiplyBA (cutlass_bellpack_lib.cu:542, -M 11): C (n x cols) = B (n x rows) * A,
+ * B and C column-major with ldb, ldc >= n. */
+int sparta_vbr_spmm_BA(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                       const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
+                       const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
+                       int64_t ldc, int precision, float* dt_ms);
 
 /* Replaces cusparse_gemm_custom_ellpack (-M 3) / compute_cutlass_bellpack (-M 8).
  * B and C row-major (cuda_utilities.cpp:1581-1591). */
@@ -246,13 +276,19 @@ int sparta_host_bellpack_free(sparta_host_bell* b);
 /* Host-only access to the schedule itself so the CPU test-suite can interpret it
  * (tests/sched_interp.py) without a GPU.  No arithmetic on matrix values happens
  * in the library on this path.  `which`: 0 segments, 1 super-rows, 2 chunks,
- * 3 items, 4 cta_ptr, 5 cta_items, 6 pack jobs, 7 run tables (record layouts: csrc/sched_types.h).
+ * 3 items, 4 cta_ptr, 5 cta_items, 6 pack jobs, 7 run tables, 8 zero jobs (record layouts:
+ * csrc/sched_types.h).
  * *data points into the plan and stays valid until sparta_plan_destroy. */
 typedef struct sparta_plan sparta_plan;
 int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_t block_rows,
                            int64_t block_col_size, const int64_t* row_part,
                            const int64_t* nzcount, const int64_t* jab, int64_t n,
                            const sparta_options* opt);
+/* the schedule of the inverted product (sparta_vbr_create_BA) */
+int sparta_vbr_plan_create_BA(sparta_plan** out, int64_t rows, int64_t cols, int64_t block_rows,
+                              int64_t block_col_size, const int64_t* row_part,
+                              const int64_t* nzcount, const int64_t* jab, int64_t n,
+                              const sparta_options* opt);
 int sparta_plan_array(sparta_plan* plan, int32_t which, const void** data, int64_t* count,
                       int32_t* record_bytes);
 int sparta_plan_stats(sparta_plan* plan, sparta_stats* out);

@@ -9,9 +9,11 @@
 //   -M 2  cusparse_spmm          cusparse_blockmat_multiplyAB      -> sparta_csr_spmm      (fp32)
 //   -M 3  cusparse_bellpack      bellpack_blockmat_multiplyAB      -> sparta_bellpack_spmm (fp16)
 //   -M 4  cublas_vbr             cublas_fixed_blocks_multiply      -> sparta_vbr_spmm      (fp16)
+//   -M 6  cublas_vbr_inverted    cublas_blockmat_multiplyBA        -> sparta_vbr_spmm_BA   (fp16)
 //   -M 7  cublas_vbr_batched     cublas_blockmat_batched           -> sparta_vbr_spmm      (tf32)
 //   -M 8  cutlass_bellpack       bellpack_cutlass_multiplyAB       -> sparta_bellpack_spmm (fp16)
 //   -M 10 cutlas_vbr             cutlas_fixed_blocks_multiply      -> sparta_vbr_spmm      (fp16)
+//   -M 11 cutlas_vbr_inverted    cutlas_blockmat_multiplyBA        -> sparta_vbr_spmm_BA   (fp16)
 //   (undefined in the reference) cublas_blockmat_multiplyAB        -> sparta_vbr_spmm, true variable heights
 //
 // Operand precision follows what each reference routine asks of its library (CUDA_R_16F for the
@@ -20,8 +22,8 @@
 // pointers in and out, alpha = beta = 1 on a caller-zeroed C, dt = CUDA-event milliseconds around
 // the compute only, any failure prints and exits like checkCudaErrors (helper_cuda.h:714-727).
 //
-// Not provided (outside the hot path): the inverted product C = B*A (-M 6, 11,
-// 12) and the dense GEMMs (-M 1, 9); they print a message and exit.
+// Not provided (outside the hot path): the batched inverted product (-M 12) and the dense GEMMs
+// (-M 1, 9); they print a message and exit.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,6 +66,15 @@ void vbr_multiply(const VBR& A, DataT* B, int B_cols, DataT_C* C, float& dt, int
     die("sparta_vbr_spmm");
 }
 
+// C = B*A: B is B_rows x A.rows, C is B_rows x A.cols, both column-major with ld = B_rows
+// (cuda_utilities.cpp:556-559,587-591)
+void vbr_multiply_BA(const VBR& A, DataT* B, int B_rows, DataT_C* C, float& dt, int precision) {
+  if (sparta_vbr_spmm_BA(A.rows, A.cols, A.block_rows, A.block_col_size,
+                         reinterpret_cast<const int64_t*>(A.row_part), reinterpret_cast<const int64_t*>(A.nzcount),
+                         reinterpret_cast<const int64_t*>(A.jab), A.mab, B, B_rows, B_rows, C, B_rows, precision, &dt))
+    die("sparta_vbr_spmm_BA");
+}
+
 }  // namespace
 
 // ---- VBR x dense ------------------------------------------------------------------------------
@@ -82,6 +93,20 @@ void cublas_blockmat_batched(const VBR& vbmatA, DataT* B, int B_cols, DataT_C* C
 
 void cutlas_fixed_blocks_multiply(const VBR& vbmatA, DataT* B, int B_cols, DataT_C* C, float& dt) {
   vbr_multiply(vbmatA, B, B_cols, C, dt, precision_or(SPARTA_FP16));
+}
+
+// ---- dense x VBR (the inverted product, -M 6 / -M 11) ------------------------------------------
+
+void cublas_blockmat_multiplyBA(const VBR& vbmatA, DataT* B, int B_rows, DataT_C* C, float& dt, int /*n_streams*/) {
+  vbr_multiply_BA(vbmatA, B, B_rows, C, dt, precision_or(SPARTA_FP16));
+}
+
+void cutlas_blockmat_multiplyBA(const VBR& vbmatA, DataT* B, int B_rows, DataT_C* C, float& dt) {
+  vbr_multiply_BA(vbmatA, B, B_rows, C, dt, precision_or(SPARTA_FP16));
+}
+
+void cutlas_blockmat_multiplyBA_streams(const VBR& vbmatA, DataT* B, int B_rows, DataT_C* C, float& dt, int /*n_streams*/) {
+  vbr_multiply_BA(vbmatA, B, B_rows, C, dt, precision_or(SPARTA_FP16));
 }
 
 // ---- Blocked-ELL x dense (B and C row-major, cuda_utilities.cpp:1581-1591) ---------------------
@@ -172,9 +197,6 @@ void pico_print_DnM(const char* Cname, int Cn, int Cm, DataT_C* C) {
 
 // ---- outside the hot path ----------------------------------------------------------------------
 
-void cublas_blockmat_multiplyBA(const VBR&, DataT*, int, DataT_C*, float&, int) { not_provided("cublas_blockmat_multiplyBA", "-M 6"); }
-void cutlas_blockmat_multiplyBA(const VBR&, DataT*, int, DataT_C*, float&) { not_provided("cutlas_blockmat_multiplyBA", "-M 11"); }
-void cutlas_blockmat_multiplyBA_streams(const VBR&, DataT*, int, DataT_C*, float&, int) { not_provided("cutlas_blockmat_multiplyBA_streams", "-"); }
 void cutlas_blockmat_batched(const VBR&, DataT*, int, DataT_C*, float&) { not_provided("cutlas_blockmat_batched", "-M 12"); }
 void cublas_dense_multiplyAB(int, int, DataT*, DataT*, int, DataT_C*, float&) { not_provided("cublas_dense_multiplyAB", "-M 1"); }
 int cutlass_dense_multiplyAB(int, int, DataT*, int, DataT*, float, float, DataT_C*, float&) { not_provided("cutlass_dense_multiplyAB", "-M 9"); }

@@ -106,6 +106,9 @@ class Oracle:
         L.oracle_vbr_multiply.restype = None
         L.oracle_vbr_multiply.argtypes = [C.c_long, C.c_long] + [C.c_void_p] * 5 + [C.c_long, C.c_long,
                                                                                      C.c_void_p, C.c_long]
+        L.oracle_vbr_multiply_BA.restype = None
+        L.oracle_vbr_multiply_BA.argtypes = [C.c_long, C.c_long, C.c_long] + [C.c_void_p] * 5 + [
+            C.c_long, C.c_long, C.c_void_p, C.c_long]
         L.oracle_csr_multiply.restype = None
         L.oracle_csr_multiply.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p, C.c_long, C.c_void_p]
@@ -149,6 +152,17 @@ class Oracle:
         self.lib.oracle_vbr_multiply(len(nz), int(v["block_col_size"]), _p(rp), _p(nz), _p(jab), _p(mab),
                                      _p(Bm), ldb, n, _p(Cm), rows)
         return Cm.reshape(n, rows)
+
+    def vbr_multiply_BA(self, v, Bt, m):
+        """C = B*A (the arithmetic cublas_blockmat_multiplyBA intends; parity unpinned, see the C
+        source).  Bt: [rows, m] (row k = column k of B); returns C as [cols, m]."""
+        rows, cols = int(v["rows"]), int(v["cols"])
+        Bt = _f(Bt).reshape(-1)
+        Cm = np.zeros(m * cols, dtype=np.float32)
+        rp, nz, jab, mab = _l(v["row_part"]), _l(v["nzcount"]), _l(v["jab"]), _f(v["mab"])
+        self.lib.oracle_vbr_multiply_BA(cols, len(nz), int(v["block_col_size"]), _p(rp), _p(nz), _p(jab),
+                                        _p(mab), _p(Bt), m, m, _p(Cm), m)
+        return Cm.reshape(cols, m)
 
     def csr_multiply(self, rows, rowptr, colind, val, pattern_only, Bm, n):
         rowptr, colind, val, Bm = _l(rowptr), _l(colind), _f(val), _f(Bm).reshape(-1)

@@ -56,6 +56,27 @@ def vbr_spmm(A: VBR, B: np.ndarray, B_cols: int, precision="bf16"):
     return Cbuf, dt.value
 
 
+def vbr_spmm_BA(A: VBR, B: np.ndarray, B_rows: int, precision="bf16"):
+    """C = B*A like cublas_blockmat_multiplyBA / cutlas_blockmat_multiplyBA (reference
+    src/cuda/cuda_utilities.cpp:553, src/cuda/cutlass_bellpack_lib.cu:542; `-M 6`, `-M 11`):
+    B is B_rows x A.rows and C is B_rows x A.cols, both column-major with ld = B_rows; the columns
+    of B follow A's blocked row order.  B is passed as the [A.rows, B_rows] array whose row k is
+    column k of B; returns (C as [A.cols, B_rows], dt_ms)."""
+    lib = _lib.load()
+    B = np.ascontiguousarray(B, dtype=np.float32).reshape(-1)
+    if B.size < A.rows * B_rows:
+        raise ValueError("B must hold B_rows * rows floats (column-major)")
+    Cbuf = np.zeros((A.cols, B_rows), dtype=np.float32)
+    dt = C.c_float(0)
+    rp, nz, jab = (np.ascontiguousarray(x, dtype=np.int64) for x in (A.row_part, A.nzcount, A.jab))
+    mab = np.ascontiguousarray(A.mab, dtype=np.float32)
+    prec = _lib.PRECISIONS[precision]
+    _lib._check(lib.sparta_vbr_spmm_BA(A.rows, A.cols, A.block_rows, A.block_col_size, _lib._ptr(rp),
+                                       _lib._ptr(nz), _lib._ptr(jab), _lib._ptr(mab), _lib._ptr(B),
+                                       B_rows, B_rows, _lib._ptr(Cbuf), B_rows, prec, C.byref(dt)))
+    return Cbuf, dt.value
+
+
 def bellpack_from_vbr(A: VBR):
     """Host repack VBR -> Blocked-ELL with the exact output of
     prepare_cusparse_BLOCKEDELLPACK (reference cuda_utilities.cpp:1656-1710).

@@ -109,6 +109,7 @@ struct sparta_handle {
   Item* d_items = nullptr;
   int32_t* d_cta_ptr = nullptr;
   int32_t* d_cta_items = nullptr;
+  ZeroJob* d_zero_jobs = nullptr;
   // CSR handles
   int64_t* d_rowptr = nullptr;
   int32_t* d_colind = nullptr;
@@ -180,6 +181,64 @@ static const char* blockrows_from_vbr(int64_t block_rows, int64_t w, const int64
   return "";
 }
 
+// A TRANSPOSED, for the inverted product C = B*A (cublas_blockmat_multiplyBA,
+// cuda_utilities.cpp:553-721): the block-rows of the operand are A's column blocks [lo, hi) --
+// `w` output rows each, the last one cols - jb*w -- and its blocks along k are A's block-rows,
+// k = A's rows in blocked order (row_part), extent = the block-row's height.  Source element (r, k)
+// of the transposed block (ib, jb) is mab[block + k + r*h]: row stride h, k stride 1.
+static const char* blockrows_from_vbr_transposed(int64_t cols, int64_t block_rows, int64_t w,
+                                                 const int64_t* row_part, const int64_t* nzcount,
+                                                 const int64_t* jab, int64_t lo, int64_t hi, BlockRows* br,
+                                                 int64_t* src_hi) {
+  const int64_t bc = (cols - 1) / w + 1;
+  if (lo < 0 || hi > bc || lo > hi) return "column-block range out of bounds";
+  br->w = w;
+  const int64_t nb = hi - lo;
+  std::vector<int64_t> count(nb + 1, 0);
+  int64_t q = 0, mab_off = 0;
+  for (int64_t b = 0; b < block_rows; ++b) {
+    const int64_t H = row_part[b + 1] - row_part[b];
+    if (H < 0 || nzcount[b] < 0) return "row_part must be non-decreasing and nzcount non-negative";
+    for (int64_t t = 0; t < nzcount[b]; ++t, ++q) {
+      const int64_t jb = jab[q];
+      if (t > 0 && jb <= jab[q - 1]) return "jab must be strictly ascending inside a block-row";
+      if (jb < 0 || jb >= bc) return "jab entry beyond the last column block";
+      if (jb >= lo && jb < hi && H > 0) ++count[jb - lo + 1];
+    }
+    mab_off += nzcount[b] * H * w;
+  }
+  *src_hi = mab_off;
+  for (int64_t j = 0; j < nb; ++j) count[j + 1] += count[j];
+  br->ptr = count;
+  const int64_t total = count[nb];
+  br->col.resize(total); br->src.resize(total);
+  br->blk_k0.resize(total); br->blk_kw.resize(total); br->blk_rs.resize(total); br->blk_ks.assign(total, 1);
+  std::vector<int64_t> fill(count.begin(), count.end() - 1);
+  q = 0; mab_off = 0;
+  for (int64_t b = 0; b < block_rows; ++b) {      // ascending b => ascending k inside every list
+    const int64_t H = row_part[b + 1] - row_part[b];
+    for (int64_t t = 0; t < nzcount[b]; ++t, ++q) {
+      const int64_t jb = jab[q];
+      if (jb >= lo && jb < hi && H > 0) {
+        const int64_t at = fill[jb - lo]++;
+        br->col[at] = b;
+        br->src[at] = mab_off + t * H * w;
+        br->blk_k0[at] = row_part[b];
+        br->blk_kw[at] = H;
+        br->blk_rs[at] = H;
+      }
+    }
+    mab_off += nzcount[b] * H * w;
+  }
+  for (int64_t j = lo; j < hi; ++j) {
+    br->row0.push_back((j - lo) * w);
+    br->height.push_back(std::min(w, cols - j * w));
+    br->rs.push_back(0);
+    br->ks.push_back(0);
+  }
+  return "";
+}
+
 static const char* blockrows_from_bell(int64_t bs, int64_t ind_rows, int64_t ind_cols,
                                        const int64_t* ind, int64_t lo, int64_t hi, BlockRows* br,
                                        int64_t* src_lo, int64_t* src_hi) {
@@ -220,7 +279,7 @@ static void free_handle(sparta_handle* h) {
   cudaStream_t s = h->stream;
   if (s) {
     dev_free(h->d_segs, s); dev_free(h->d_srows, s); dev_free(h->d_chunks, s); dev_free(h->d_tables, s);
-    dev_free(h->d_a, s); dev_free(h->d_items, s); dev_free(h->d_cta_ptr, s); dev_free(h->d_cta_items, s);
+    dev_free(h->d_a, s); dev_free(h->d_items, s); dev_free(h->d_cta_ptr, s); dev_free(h->d_cta_items, s); dev_free(h->d_zero_jobs, s);
     dev_free(h->d_rowptr, s); dev_free(h->d_colind, s); dev_free(h->d_val, s); dev_free(h->d_row_order, s);
     dev_free(h->d_B, s); dev_free(h->d_C, s);
     cudaStreamSynchronize(s);   // the blocks are back in the pool before the stream goes away
@@ -296,6 +355,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->sopt.sort_rows = o.row_order != 1;
   h->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
   h->sopt.max_chain = o.max_chain;
+  h->sopt.split = o.split_k;
   h->panel_stages = o.panel_stages;
   h->a_ring_bytes = ring_bytes_for(o.panel_stages);
   h->accumulate = o.accumulate ? 1 : 0;
@@ -411,6 +471,44 @@ int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t b
                       int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                       const int64_t* jab, const float* mab, const sparta_options* opt) {
   return vbr_create_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false);
+}
+
+static int vbr_create_ba_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                              int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                              const int64_t* jab, const float* mab, const sparta_options* opt,
+                              bool defer_sync) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows <= 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part || (block_rows && !nzcount))
+    return fail(SPARTA_ERR_INVALID, "invalid VBR dimensions or NULL index arrays");
+  if (block_rows > 0 && row_part[block_rows] != rows)
+    return fail(SPARTA_ERR_INVALID, "row_part[block_rows] must equal rows (VBR::partition_check)");
+  sparta_options o;
+  resolve_options(opt, &o);
+  const int64_t bc = (cols - 1) / block_col_size + 1;
+  const int64_t lo = o.block_row_begin;
+  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : bc;
+  BlockRows br;
+  int64_t src_hi = 0;
+  const char* e = blockrows_from_vbr_transposed(cols, block_rows, block_col_size, row_part, nzcount, jab, lo, hi,
+                                                &br, &src_hi);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  if (src_hi > 0 && !mab) return fail(SPARTA_ERR_INVALID, "mab is NULL");
+  // the operand's k runs over A's rows; B (n x rows) and C (n x cols) column-major are the
+  // row-major [rows][n] and [cols][n] operands of C^T = A^T * B^T
+  const int rc = create_common(out, br, mab, src_hi, rows, o, 1, defer_sync);
+  if (rc == SPARTA_OK) {   // FLOP accounting on the reference's nztot (full-width last column block)
+    int64_t blocks = 0;
+    for (int64_t t = 0; t < static_cast<int64_t>(br.blk_kw.size()); ++t) blocks += br.blk_kw[t];
+    (*out)->st.nztot = blocks * block_col_size;
+  }
+  return rc;
+}
+
+int sparta_vbr_create_BA(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
+                         int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
+                         const int64_t* jab, const float* mab, const sparta_options* opt) {
+  return vbr_create_ba_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false);
 }
 
 static int bellpack_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t ell_blocksize,
@@ -583,6 +681,9 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
       const char* serr = build_assignment(h->st, h->sopt, n, h->cols, &h->as);
       if (*serr) return fail(SPARTA_ERR_INVALID, serr);
       dev_free(h->d_items, h->stream); dev_free(h->d_cta_ptr, h->stream); dev_free(h->d_cta_items, h->stream);
+      dev_free(h->d_zero_jobs, h->stream);
+      h->d_zero_jobs = nullptr;
+      if (!h->as.zero_jobs.empty()) CU_TRY(upload_vec(h->as.zero_jobs, &h->d_zero_jobs, h->stream));
       CU_TRY(upload_vec(h->as.items, &h->d_items, h->stream));
       CU_TRY(upload_vec(h->as.cta_ptr, &h->d_cta_ptr, h->stream));
       CU_TRY(upload_vec(h->as.cta_items, &h->d_cta_items, h->stream));
@@ -681,6 +782,11 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   p.acc_stages = h->st.master_col > 0 ? 1 : 512 / h->st.acc_cols;
   p.acc_stage_cols = h->st.acc_cols;
   const char* err = "";
+  if (!h->as.zero_jobs.empty() && !h->accumulate) {
+    // split pieces add partial sums: their C tiles start from zero (C := A*B semantics)
+    const cudaError_t ez = zero_c_tiles_launch(p, h->d_zero_jobs, static_cast<int>(h->as.zero_jobs.size()), h->stream);
+    if (ez != cudaSuccess) return fail_cuda(ez, "zeroing the split C tiles");
+  }
   cudaError_t e = spmm_launch(p, h->d_B, h->cols, h->ldk, h->sopt.precision, h->as.grid, h->stream, &err);
   if (e != cudaSuccess) return fail_cuda(e, err);
   ++h->launches;
@@ -751,6 +857,9 @@ static void fill_stats(const Structure& st, const Assignment& as, int64_t cols, 
   s->sched_imbalance = as.mean_cta_cost > 0 ? as.max_cta_cost / as.mean_cta_cost : 1.0;
   s->team = as.team;
   s->cta_pair = st.pair;
+  s->split_pieces = as.split_pieces;
+  s->zero_tiles = static_cast<int32_t>(as.zero_jobs.size());
+  s->sched_max_cycles = as.max_cta_cost;
 }
 
 int sparta_get_stats(sparta_handle* h, sparta_stats* out) {
@@ -833,6 +942,19 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
   o.precision = precision;
   return one_shot("sparta_vbr_spmm", [&](sparta_handle** h) {
     return vbr_create_impl(h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o, true);
+  }, B, ldb, n, C, ldc, dt_ms);
+}
+
+int sparta_vbr_spmm_BA(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                       const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
+                       const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
+                       int64_t ldc, int precision, float* dt_ms) {
+  sparta_options o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  o.precision = precision;
+  return one_shot("sparta_vbr_spmm_BA", [&](sparta_handle** h) {
+    return vbr_create_ba_impl(h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o, true);
   }, B, ldb, n, C, ldc, dt_ms);
 }
 
@@ -1009,11 +1131,49 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
   p->sopt.sort_rows = o.row_order != 1;
   p->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
   p->sopt.max_chain = o.max_chain;
+  p->sopt.split = o.split_k;
   p->cols = cols; p->block_rows = br.count(); p->n = n;
   p->panel_stages = o.panel_stages;
   p->a_ring_bytes = ring_bytes_for(o.panel_stages);
   e = build_structure(br, p->sopt, &p->st);
   if (!*e) e = build_assignment(p->st, p->sopt, n, cols, &p->as);
+  if (*e) { delete p; return fail(SPARTA_ERR_INVALID, e); }
+  *out = p;
+  return SPARTA_OK;
+}
+
+int sparta_vbr_plan_create_BA(sparta_plan** out, int64_t rows, int64_t cols, int64_t block_rows,
+                              int64_t block_col_size, const int64_t* row_part,
+                              const int64_t* nzcount, const int64_t* jab, int64_t n,
+                              const sparta_options* opt) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows <= 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part || (block_rows && !nzcount))
+    return fail(SPARTA_ERR_INVALID, "invalid VBR dimensions or NULL index arrays");
+  sparta_options o;
+  resolve_options(opt, &o);
+  const int64_t bc = (cols - 1) / block_col_size + 1;
+  BlockRows br;
+  int64_t src_hi = 0;
+  const char* e = blockrows_from_vbr_transposed(cols, block_rows, block_col_size, row_part, nzcount, jab,
+                                                o.block_row_begin, o.block_row_end > 0 ? o.block_row_end : bc,
+                                                &br, &src_hi);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  sparta_plan* p = new sparta_plan();
+  p->sopt.precision = o.precision;
+  p->sopt.seg_rows = o.seg_rows;
+  p->sopt.acc_cols = o.acc_cols;
+  p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  p->sopt.pair = o.cta_pair != 1;
+  p->sopt.sort_rows = o.row_order != 1;
+  p->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
+  p->sopt.max_chain = o.max_chain;
+  p->sopt.split = o.split_k;
+  p->cols = rows; p->block_rows = br.count(); p->n = n;
+  p->panel_stages = o.panel_stages;
+  p->a_ring_bytes = ring_bytes_for(o.panel_stages);
+  e = build_structure(br, p->sopt, &p->st);
+  if (!*e) e = build_assignment(p->st, p->sopt, n, rows, &p->as);
   if (*e) { delete p; return fail(SPARTA_ERR_INVALID, e); }
   *out = p;
   return SPARTA_OK;
@@ -1038,6 +1198,7 @@ int sparta_plan_array(sparta_plan* plan, int32_t which, const void** data, int64
     case 5: PLAN_ARR(plan->as.cta_items, int32_t);
     case 6: PLAN_ARR(plan->st.jobs, PackJob);
     case 7: PLAN_ARR(plan->st.tables, uint32_t);
+    case 8: PLAN_ARR(plan->as.zero_jobs, ZeroJob);
   }
 #undef PLAN_ARR
   return fail(SPARTA_ERR_INVALID, "unknown plan array id");

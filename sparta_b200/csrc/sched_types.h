@@ -58,14 +58,28 @@ constexpr int kTableBytes = kTableWords * 4;   // 272: the largest table (32 run
 // pass into a MASTER copy of the accumulator kept in the other half of TMEM with round-to-nearest
 // fp32 adds, and only the last pass writes C.  This bounds the error of the tensor core's
 // truncating fp32 accumulation, which otherwise grows linearly with the number of MMAs.
+//
+// A (super-row, column tile) may also be SPLIT along its chunk list between several workers
+// (schedule.cpp, build_assignment): when a shard holds too few super-rows to fill the grid -- one
+// rank of an 8-GPU run owns ~10 super-rows x 8 column tiles for 74 CTA pairs -- the chunk lists are
+// laid end to end and cut into equal-cost pieces.  A piece that does not cover the whole list adds
+// its partial sums to C with fp32 reductions (kItemAtomic); the tiles those pieces write are
+// zeroed by a small kernel before the launch (Assignment::zero_jobs).
 constexpr uint32_t kItemNotFirst = 1u << 31;   // fold the master copy into this pass's result
 constexpr uint32_t kItemNotLast  = 1u << 30;   // store the result to the master copy, not to C
-constexpr uint32_t kItemCountMask = (1u << 30) - 1;
+constexpr uint32_t kItemAtomic   = 1u << 29;   // C += result with red.global.add (a split piece)
+constexpr uint32_t kItemCountMask = (1u << 29) - 1;
 struct Item {
   int32_t srow;       // super-row id
   int32_t j0;         // first column of B/C of this column tile
   int32_t chunk_off;  // first chunk of the pass, relative to SuperRow::chunk_begin
   uint32_t count;     // chunks in the pass | kItemNotFirst | kItemNotLast
+};
+
+// A C tile that split pieces accumulate into: the rows of super-row `srow`, columns [j0, j0+tile).
+struct ZeroJob {
+  int32_t srow;
+  int32_t j0;
 };
 
 // One packed A image = h_pad rows x 128 bytes in the K-major SWIZZLE_128B

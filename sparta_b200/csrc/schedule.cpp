@@ -17,6 +17,28 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static const char* build_structure_for(const BlockRows& br, const ScheduleOptions& opt, int64_t chain,
                                        Structure* out);
 
+// Cuts chunks [c0, c1) of the super-row starting at chunks[begin] into passes of at most `chain`
+// MMAs each (balanced; chain <= 0: one pass).  Appends the first chunk of every pass to *offs.
+static void cut_passes(const std::vector<Chunk>& chunks, int64_t begin, int32_t c0, int32_t c1,
+                       int64_t chain, std::vector<int32_t>* offs, int64_t* longest) {
+  int64_t total = 0;
+  for (int32_t c = c0; c < c1; ++c) total += chunks[begin + c].ksteps;
+  const int64_t passes = chain > 0 ? std::max<int64_t>(1, (total + chain - 1) / chain) : 1;
+  const int64_t target = (total + passes - 1) / passes;
+  int64_t run = 0;
+  offs->push_back(c0);
+  for (int32_t c = c0; c < c1; ++c) {
+    const int64_t k = chunks[begin + c].ksteps;
+    if (run > 0 && run + k > target) {
+      if (longest) *longest = std::max(*longest, run);
+      offs->push_back(c);
+      run = 0;
+    }
+    run += k;
+  }
+  if (longest) *longest = std::max(*longest, run);
+}
+
 // chain limit in MMAs per accumulator: tf32 sums are held to <= 1e-5, and the tensor
 // core's fp32 accumulation truncates (measured: 5.6e-5 relative on an all-positive chain of ~8000
 // MMAs), so tf32 bounds the chain by default; bf16 / fp16 (tolerance 2e-2) do not.
@@ -41,7 +63,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
   st.pair = opt.pair ? 1 : 0;
   st.acc_cols = opt.acc_cols;
   st.master_col = chain > 0 ? 256 : 0;
-  std::vector<int32_t> ksteps_of;   // per chunk of the current super-row
+  st.chain = chain;
   if (br.w <= 0) return "column block size must be positive";
   if (opt.seg_rows < 16 || opt.seg_rows > 256 || opt.seg_rows % 16) return "seg_rows must be a multiple of 16 in [16,256]";
   if (opt.acc_cols != 256 && opt.acc_cols != 512) return "acc_cols must be 256 or 512";
@@ -79,7 +101,8 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
     if (H <= 0) continue;
     st.rows = std::max<int64_t>(st.rows, br.row0[b] + H);
     if (br.row0[b] + H > INT32_MAX) return "shard has more than 2^31 rows";
-    st.nztot += nblk * H * br.w;
+    if (br.blk_kw.empty()) st.nztot += nblk * H * br.w;
+    else for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) st.nztot += H * br.blk_kw[q];
     for (int64_t off = 0; off < H; off += opt.seg_rows) {
       Segment sg;
       sg.h = static_cast<int32_t>(std::min<int64_t>(opt.seg_rows, H - off));
@@ -132,7 +155,9 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         merged.emplace_back(br.col[q], static_cast<int>(s - s0));
     }
     std::sort(merged.begin(), merged.end());
-    double cost = 200.0 + 6.0 * cols;  // pipeline fill + epilogue drain
+    // pipeline fill + epilogue drain
+    const double fixed = 400.0 + 14.0 * cols;
+    double cost = fixed;
     size_t i = 0;
     while (i < merged.size()) {
       const int64_t jb = merged[i].first;
@@ -149,13 +174,15 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
       uint32_t rows_present = 0;
       for (size_t t = i; t < i1; ++t) rows_present += st.segs[s0 + merged[t].second].h_pad;
       // K slabs of this column block: start at the 16-byte aligned k at or below jb*w
-      const int64_t kblk = jb * br.w;
+      const int64_t q_any = slot_of[merged[i].second] - br.col.data();   // same k range for every member
+      const int64_t kblk = br.blk_k0.empty() ? jb * br.w : br.blk_k0[q_any];
+      const int64_t kw = br.blk_kw.empty() ? br.w : br.blk_kw[q_any];
       const int64_t ka = kblk / kalign * kalign;
       const int shift = static_cast<int>(kblk - ka);
-      const int64_t atoms = (shift + br.w + katom - 1) / katom;
+      const int64_t atoms = (shift + kw + katom - 1) / katom;
       for (int64_t a = 0; a < atoms; ++a) {
         const int64_t k_lo = a * katom - shift;  // block-local k of image column 0
-        const int k_used = static_cast<int>(std::min<int64_t>(katom, br.w - k_lo));
+        const int k_used = static_cast<int>(std::min<int64_t>(katom, kw - k_lo));
         Chunk ch{};
         const int64_t k0 = ka + a * katom;
         if (k0 > INT32_MAX) return "k index exceeds 2^31";
@@ -190,13 +217,13 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
               const int r0 = std::max(lo, cta * half), r1 = std::min(hi, (cta + 1) * half);
               if (r0 >= r1) continue;
               PackJob job;
-              job.src_rs = br.rs[b];
-              job.src_ks = br.ks[b];
+              job.src_rs = br.blk_rs.empty() ? br.rs[b] : br.blk_rs[q];
+              job.src_ks = br.blk_ks.empty() ? br.ks[b] : br.blk_ks[q];
               job.src_base = br.src[q] + (seg_src[s].row_off + (r0 - lo)) * job.src_rs;
               job.h = std::max(0, std::min(st.segs[s].h - (r0 - lo), r1 - r0));
               job.h_pad = r1 - r0;
               job.k_lo = static_cast<int32_t>(k_lo);
-              job.k_w = static_cast<int32_t>(br.w);
+              job.k_w = static_cast<int32_t>(kw);
               job.pad_[0] = job.pad_[1] = job.pad_[2] = 0;
               job.dst_off16 = static_cast<uint32_t>((chunk_base + cta * share + cursor[cta]) >> 4);
               st.jobs.push_back(job);
@@ -217,33 +244,18 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         // modelled cycles per CTA: tensor pipe N/2 per K step; L2 -> smem at ~40 B/cycle/SM
         const double tensor = ch.ksteps * (rows_present * 0.5);
         const double memory = (kPanelBytes + share) / 40.0;
-        cost += std::max(tensor, memory) + 30.0;
+        st.chunk_cost.push_back(static_cast<float>(std::max(tensor, memory) + 30.0));
+        cost += st.chunk_cost.back();
       }
       i = i1;
     }
     sr.chunk_count = static_cast<int32_t>(st.chunks.size()) - sr.chunk_begin;
     // passes: balanced cuts so that no pass issues more than `chain` MMAs into an accumulator
     st.pass_ptr.push_back(static_cast<int32_t>(st.pass_off.size()));
-    {
-      int64_t total = 0;
-      for (int32_t c = 0; c < sr.chunk_count; ++c) total += st.chunks[sr.chunk_begin + c].ksteps;
-      const int64_t passes = chain > 0 ? std::max<int64_t>(1, (total + chain - 1) / chain) : 1;
-      const int64_t target = (total + passes - 1) / passes;
-      int64_t run = 0;
-      st.pass_off.push_back(0);
-      for (int32_t c = 0; c < sr.chunk_count; ++c) {
-        const int64_t k = st.chunks[sr.chunk_begin + c].ksteps;
-        if (run > 0 && run + k > target) {
-          st.max_chain_seen = std::max(st.max_chain_seen, run);
-          st.pass_off.push_back(c);
-          run = 0;
-        }
-        run += k;
-      }
-      st.max_chain_seen = std::max(st.max_chain_seen, run);
-    }
+    cut_passes(st.chunks, sr.chunk_begin, 0, sr.chunk_count, chain, &st.pass_off, &st.max_chain_seen);
     st.srows.push_back(sr);
     st.srow_cost.push_back(cost);
+    st.srow_fixed.push_back(fixed);
     s0 = s1;
   }
   st.pass_ptr.push_back(static_cast<int32_t>(st.pass_off.size()));
@@ -258,29 +270,27 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
 // so HBM sees B about once and A once per group instead of once per column tile.  Inside a
 // group the workers form TEAMS of `team` = group_tiles workers: a team walks the same sequence
 // of super-rows side by side, one column tile each, so a super-row's A images are fetched from
-// HBM by whichever member gets there first and hit in L2 for the others.  Super-rows are
-// list-scheduled, heaviest first, onto the team that frees up first (modelled cost).
-const char* build_assignment(const Structure& st, const ScheduleOptions& opt, int64_t n,
-                             int64_t k_total, Assignment* out) {
-  Assignment& as = *out;
-  as = Assignment();
-  const int tile = st.pair ? 2 * kTileJ : kTileJ;
-  if (n <= 0 || n > INT32_MAX - tile) return "invalid number of B columns";
-  const int64_t tiles = (n + tile - 1) / tile;
-  const int64_t n_srows = static_cast<int64_t>(st.srows.size());
-  const int64_t n_items = static_cast<int64_t>(st.pass_off.size()) * tiles;   // one item per pass
-  if (n_items > INT32_MAX) return "too many work items";
-  int workers = std::max(1, opt.num_ctas / (st.pair ? 2 : 1));
-  workers = static_cast<int>(std::min<int64_t>(workers, std::max<int64_t>(n_srows * tiles, 1)));
-  as.workers = n_items ? workers : 0;
-  as.grid = as.workers * (st.pair ? 2 : 1);
-  as.cta_ptr.assign(as.workers + 1, 0);
-  if (n_items == 0) return "";
+// HBM by whichever member gets there first and hit in L2 for the others.
+//
+// Two ways of handing the (group, super-row) units to the teams:
+//   whole units -- list-scheduled, heaviest first, onto the team that frees up first.  Right when
+//     there are many more units than teams (a whole matrix on one GPU: 516 units for 37 teams).
+//   split units -- the units' chunk lists are laid end to end and cut into one equal-cost piece
+//     per team ("stream-K" along the block-row's column-block list).  Right when a shard holds few
+//     super-rows (one rank of an 8-GPU run: ~40 units for 37 teams, max/mean load 1.6-1.9 with
+//     whole units).  A piece of a cut unit adds its partial sums to C with fp32 reductions.
+namespace {
 
-  // column tiles per group: the largest divisor of the worker count whose slab fits
-  const double tile_bytes = static_cast<double>(k_total) * tile * prec_esize(opt.precision);
-  int64_t fit = std::max<int64_t>(1, static_cast<int64_t>(opt.l2_slab_bytes / std::max(tile_bytes, 1.0)));
-  fit = std::min(fit, tiles);
+struct TeamPiece { int32_t group, srow, c0, c1; bool partial; };
+
+struct TeamPlan {
+  int workers = 0, team = 1;
+  std::vector<std::vector<TeamPiece>> per_team;
+  double max_cost = 0, mean_cost = 0;
+  int cut_units = 0;
+};
+
+int pick_team(int workers, int64_t tiles, int64_t fit) {
   int team = 1;
   for (int t = 1; t <= workers && t <= fit; ++t)
     if (workers % t == 0) team = t;
@@ -290,55 +300,208 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
     for (int t = 1; t <= tiles; ++t)
       if (workers % t == 0 && tiles % t == 0) team = t;
   }
-  as.team = team;
-  as.group_tiles = team;
-  const int n_teams = workers / team;
+  return team;
+}
+
+void finish_costs(TeamPlan* tp, const std::vector<double>& load) {
+  double total = 0;
+  for (double l : load) {
+    tp->max_cost = std::max(tp->max_cost, l);
+    total += l;
+  }
+  tp->mean_cost = load.empty() ? 0.0 : total / load.size();
+}
+
+void plan_whole(const Structure& st, const std::vector<int32_t>& by_cost, int64_t groups, TeamPlan* tp) {
+  const int n_teams = tp->workers / tp->team;
+  tp->per_team.assign(n_teams, {});
+  typedef std::pair<double, int> Load;
+  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  for (int t = 0; t < n_teams; ++t) heap.push(Load(0.0, t));
+  for (int64_t g = 0; g < groups; ++g)
+    for (int32_t s : by_cost) {
+      Load l = heap.top();
+      heap.pop();
+      tp->per_team[l.second].push_back({static_cast<int32_t>(g), s, 0, st.srows[s].chunk_count, false});
+      l.first += st.srow_cost[s];
+      heap.push(l);
+    }
+  std::vector<double> load;
+  while (!heap.empty()) { load.push_back(heap.top().first); heap.pop(); }
+  finish_costs(tp, load);
+}
+
+// Greedy fill of ONE column group: teams take the super-rows in sequence until they hold `target`
+// cycles; a super-row that does not fit is cut at the chunk where the team is full.  The last
+// team takes whatever is left.
+void fill_split(const Structure& st, const std::vector<int32_t>& by_cost, const std::vector<double>& prefix,
+                int n_teams, double target, std::vector<std::vector<TeamPiece>>* per_team,
+                std::vector<double>* load) {
+  const int32_t kMinChunks = 8;        // never cut off a piece shorter than this
+  per_team->assign(n_teams, {});
+  load->assign(n_teams, 0.0);
+  int t = 0;
+  for (int32_t s : by_cost) {
+    const SuperRow& sr = st.srows[s];
+    const double* pf = prefix.data() + sr.chunk_begin;   // pf[c] - pf[0] = cost of the chunks before c
+    const double fixed = st.srow_fixed[s];
+    int32_t c = 0;
+    if (sr.chunk_count == 0) {   // no blocks at all: the item only writes zeros
+      if (t < n_teams - 1 && (*load)[t] + fixed > target) ++t;
+      (*per_team)[t].push_back({0, s, 0, 0, false});
+      (*load)[t] += fixed;
+    }
+    while (c < sr.chunk_count) {
+      const double rest = pf[sr.chunk_count] - pf[c];
+      const double room = target - (*load)[t] - fixed;
+      if (t == n_teams - 1 || rest <= room) {
+        (*per_team)[t].push_back({0, s, c, sr.chunk_count, false});
+        (*load)[t] += fixed + rest;
+        break;
+      }
+      // largest e with cost of [c, e) <= room
+      const int32_t e = static_cast<int32_t>(
+          std::upper_bound(pf + c, pf + sr.chunk_count + 1, pf[c] + std::max(room, 0.0)) - pf) - 1;
+      if (e - c >= kMinChunks && sr.chunk_count - e >= kMinChunks) {
+        (*per_team)[t].push_back({0, s, c, e, true});
+        (*load)[t] += fixed + (pf[e] - pf[c]);
+        c = e;
+      }
+      ++t;   // this team is full (or cannot take a piece worth cutting)
+    }
+  }
+  // a piece is partial iff it is not the whole chunk list of its super-row
+  for (auto& list : *per_team)
+    for (auto& pc : list) pc.partial = pc.c0 != 0 || pc.c1 != st.srows[pc.srow].chunk_count;
+}
+
+// The cut is made inside ONE column group and repeated for every group, so that all teams stay in
+// the same group at the same time and its B slab stays L2-resident (cutting the concatenation of
+// all groups instead put the teams in different groups: measured 30 % slower at 2 shards, the B
+// panels came from HBM).  Odd groups hand the pieces out in reverse team order to even out what
+// the greedy fill leaves to the last team.
+void plan_split(const Structure& st, const std::vector<int32_t>& by_cost, int64_t groups, TeamPlan* tp) {
+  const int n_teams = tp->workers / tp->team;
+  std::vector<double> prefix(st.chunk_cost.size() + 1, 0.0);
+  for (size_t c = 0; c < st.chunk_cost.size(); ++c) prefix[c + 1] = prefix[c] + st.chunk_cost[c];
+  double total = 0, biggest = 0;
+  for (int32_t s : by_cost) { total += st.srow_cost[s]; biggest = std::max(biggest, st.srow_cost[s]); }
+  // Every cut re-pays the fixed part of the unit it cuts and pieces have a minimum length, so the
+  // load the greedy fill ends up with is not a monotone function of the target: scan a ladder of
+  // targets from the ideal mean upwards and keep the fill with the smallest maximum load.
+  const double lo = total / n_teams, hi = std::max(2.0 * lo, lo + biggest);
+  std::vector<std::vector<TeamPiece>> best, cur;
+  std::vector<double> best_load, cur_load;
+  double best_worst = 0;
+  for (double target = lo; ; target *= 1.01) {
+    const bool last = target >= hi;
+    fill_split(st, by_cost, prefix, n_teams, last ? hi : target, &cur, &cur_load);
+    const double worst = *std::max_element(cur_load.begin(), cur_load.end());
+    if (best.empty() || worst < best_worst) {
+      best.swap(cur);
+      best_load.swap(cur_load);
+      best_worst = worst;
+    }
+    if (last) break;
+  }
+  tp->per_team.assign(n_teams, {});
+  std::vector<double> load(n_teams, 0.0);
+  for (int64_t g = 0; g < groups; ++g)
+    for (int t = 0; t < n_teams; ++t) {
+      const int src = (g & 1) ? n_teams - 1 - t : t;
+      for (TeamPiece pc : best[src]) {
+        pc.group = static_cast<int32_t>(g);
+        tp->per_team[t].push_back(pc);
+        if (pc.partial && pc.c0 == 0) ++tp->cut_units;
+      }
+      load[t] += best_load[src];
+    }
+  finish_costs(tp, load);
+}
+
+}  // namespace
+
+const char* build_assignment(const Structure& st, const ScheduleOptions& opt, int64_t n,
+                             int64_t k_total, Assignment* out) {
+  Assignment& as = *out;
+  as = Assignment();
+  const int tile = st.pair ? 2 * kTileJ : kTileJ;
+  if (n <= 0 || n > INT32_MAX - tile) return "invalid number of B columns";
+  const int64_t tiles = (n + tile - 1) / tile;
+  const int64_t n_srows = static_cast<int64_t>(st.srows.size());
+  if (static_cast<int64_t>(st.pass_off.size()) * tiles > INT32_MAX / 2) return "too many work items";
+  const int all_workers = std::max(1, opt.num_ctas / (st.pair ? 2 : 1));
+  as.cta_ptr.assign(1, 0);
+  if (n_srows == 0) return "";
+
+  // column tiles per group: the largest divisor of the worker count whose slab fits
+  const double tile_bytes = static_cast<double>(k_total) * tile * prec_esize(opt.precision);
+  int64_t fit = std::max<int64_t>(1, static_cast<int64_t>(opt.l2_slab_bytes / std::max(tile_bytes, 1.0)));
+  fit = std::min(fit, tiles);
 
   std::vector<int32_t> by_cost(n_srows);
   for (int64_t s = 0; s < n_srows; ++s) by_cost[s] = static_cast<int32_t>(s);
   std::stable_sort(by_cost.begin(), by_cost.end(),
                    [&](int32_t a, int32_t b) { return st.srow_cost[a] > st.srow_cost[b]; });
 
-  typedef std::pair<double, int> Load;
-  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-  for (int t = 0; t < n_teams; ++t) heap.push(Load(0.0, t));
-  std::vector<std::vector<int32_t>> per_worker(workers);
-  as.items.reserve(n_items);
-  for (int64_t t0 = 0; t0 < tiles; t0 += team) {
-    const int in_group = static_cast<int>(std::min<int64_t>(team, tiles - t0));
-    for (int32_t s : by_cost) {
-      Load l = heap.top();
-      heap.pop();
-      const int32_t p0 = st.pass_ptr[s], p1 = st.pass_ptr[s + 1];
-      const int32_t n_chunks = st.srows[s].chunk_count;
+  TeamPlan whole, split;
+  whole.workers = static_cast<int>(std::min<int64_t>(all_workers, n_srows * tiles));
+  whole.team = pick_team(whole.workers, tiles, fit);
+  plan_whole(st, by_cost, (tiles + whole.team - 1) / whole.team, &whole);
+  const TeamPlan* tp = &whole;
+  if (opt.split != 1) {
+    int64_t n_chunks = 0;
+    for (const SuperRow& sr : st.srows) n_chunks += sr.chunk_count;
+    // no more workers than pieces of >= 16 chunks
+    split.workers = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(all_workers, n_chunks * tiles / 16)));
+    split.team = pick_team(split.workers, tiles, fit);
+    plan_split(st, by_cost, (tiles + split.team - 1) / split.team, &split);
+    const bool pays = split.max_cost < 0.95 * whole.max_cost;   // the worker that finishes last sets the time
+    if (opt.split == 2 || pays) tp = &split;
+  }
+
+  as.workers = tp->workers;
+  as.team = as.group_tiles = tp->team;
+  as.grid = as.workers * (st.pair ? 2 : 1);
+  as.max_cta_cost = tp->max_cost;
+  as.mean_cta_cost = tp->mean_cost;
+  std::vector<std::vector<int32_t>> per_worker(as.workers);
+  std::vector<int32_t> offs;
+  for (size_t t = 0; t < tp->per_team.size(); ++t)
+    for (const TeamPiece& pc : tp->per_team[t]) {
+      const int64_t t0 = static_cast<int64_t>(pc.group) * tp->team;
+      const int in_group = static_cast<int>(std::min<int64_t>(tp->team, tiles - t0));
+      offs.clear();
+      if (pc.partial) {
+        cut_passes(st.chunks, st.srows[pc.srow].chunk_begin, pc.c0, pc.c1, st.chain, &offs, nullptr);
+      } else {
+        offs.assign(st.pass_off.begin() + st.pass_ptr[pc.srow], st.pass_off.begin() + st.pass_ptr[pc.srow + 1]);
+      }
       for (int m = 0; m < in_group; ++m) {
-        for (int32_t ps = p0; ps < p1; ++ps) {   // the passes of one (super-row, tile) stay together
-          const int32_t off = st.pass_off[ps];
-          const int32_t end = ps + 1 < p1 ? st.pass_off[ps + 1] : n_chunks;
+        const int32_t j0 = static_cast<int32_t>((t0 + m) * tile);
+        for (size_t ps = 0; ps < offs.size(); ++ps) {   // the passes of one piece stay together
+          const int32_t off = offs[ps];
+          const int32_t end = ps + 1 < offs.size() ? offs[ps + 1] : pc.c1;
           uint32_t count = static_cast<uint32_t>(end - off);
-          if (ps > p0) count |= kItemNotFirst;
-          if (ps + 1 < p1) count |= kItemNotLast;
-          per_worker[l.second * team + m].push_back(static_cast<int32_t>(as.items.size()));
-          as.items.push_back(Item{s, static_cast<int32_t>((t0 + m) * tile), off, count});
+          if (ps > 0) count |= kItemNotFirst;
+          if (ps + 1 < offs.size()) count |= kItemNotLast;
+          else if (pc.partial) count |= kItemAtomic;
+          per_worker[t * tp->team + m].push_back(static_cast<int32_t>(as.items.size()));
+          as.items.push_back(Item{pc.srow, j0, off, count});
+        }
+        if (pc.partial) {
+          ++as.split_pieces;
+          if (pc.c0 == 0) as.zero_jobs.push_back(ZeroJob{pc.srow, j0});
         }
       }
-      l.first += st.srow_cost[s];
-      heap.push(l);
     }
-  }
-  double total = 0;
-  while (!heap.empty()) {
-    as.max_cta_cost = std::max(as.max_cta_cost, heap.top().first);
-    total += heap.top().first;
-    heap.pop();
-  }
-  as.mean_cta_cost = total / n_teams;
-  as.cta_items.reserve(n_items);
-  for (int c = 0; c < workers; ++c) {
+  as.cta_ptr.assign(as.workers + 1, 0);
+  as.cta_items.reserve(as.items.size());
+  for (int c = 0; c < as.workers; ++c) {
     as.cta_ptr[c] = static_cast<int32_t>(as.cta_items.size());
     as.cta_items.insert(as.cta_items.end(), per_worker[c].begin(), per_worker[c].end());
   }
-  as.cta_ptr[workers] = static_cast<int32_t>(as.cta_items.size());
+  as.cta_ptr[as.workers] = static_cast<int32_t>(as.cta_items.size());
   return "";
 }
 

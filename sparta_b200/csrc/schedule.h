@@ -18,6 +18,13 @@ struct BlockRows {
   std::vector<int64_t> src;       // element offset of the block's (0,0) entry in the fp32 source
   std::vector<int64_t> rs;        // per block-row: element stride between rows of a block
   std::vector<int64_t> ks;        // per block-row: element stride between k of a block
+  // Optional per-block overrides (empty = the defaults above).  They describe A TRANSPOSED, the
+  // operand of the inverted product C = B*A: its block-rows are A's column blocks and its
+  // "column blocks" are A's block-rows, whose extents along k are the variable heights.
+  std::vector<int64_t> blk_k0;    // first k of the block (default col * w)
+  std::vector<int64_t> blk_kw;    // extent of the block along k (default w)
+  std::vector<int64_t> blk_rs;    // element stride between rows of the block (default rs[b])
+  std::vector<int64_t> blk_ks;    // element stride between k of the block (default ks[b])
   int64_t count() const { return static_cast<int64_t>(height.size()); }
 };
 
@@ -30,6 +37,7 @@ struct ScheduleOptions {
   int sort_rows = 1;       // 1: group block-rows of similar nonzero-block count into super-rows
   int64_t l2_slab_bytes = 64ll << 20;  // B columns kept L2-resident at a time (see build_assignment)
   int max_chain = 0;       // longest accumulation chain in tcgen05.mma instructions (0: default, -1: unlimited)
+  int split = 0;           // chunk lists split between workers: 0 when the model says it pays, 1 never, 2 always
 };
 
 struct Structure {           // independent of the number of B columns
@@ -38,7 +46,10 @@ struct Structure {           // independent of the number of B columns
   std::vector<Chunk>    chunks;
   std::vector<PackJob>  jobs;
   std::vector<uint32_t> tables;      // run tables of all chunks, back to back (see sched_types.h)
-  std::vector<double>   srow_cost;   // modelled tensor cycles per column tile
+  std::vector<double>   srow_cost;   // modelled SM cycles per column tile (fixed part + chunks)
+  std::vector<float>    chunk_cost;  // modelled SM cycles of every chunk
+  std::vector<double>   srow_fixed;  // per super-row: pipeline fill + epilogue part of srow_cost
+  int64_t chain = -1;                // accumulation-chain bound the passes were cut for (-1: none)
   std::vector<int32_t>  pass_ptr;    // [srows + 1] ranges into pass_off
   std::vector<int32_t>  pass_off;    // per pass: first chunk (relative to the super-row), see Item
   int master_col = 0;                // > 0: TMEM column of the master accumulators (bounded chains)
@@ -82,6 +93,8 @@ struct Assignment {          // depends on n (columns of B) and the grid
   int workers = 0;
   int team = 1;                     // workers walking the same super-row sequence side by side
   int group_tiles = 1;              // column tiles per L2-resident group
+  std::vector<ZeroJob> zero_jobs;   // C tiles written by split pieces (zeroed before every launch)
+  int split_pieces = 0;             // items that carry kItemAtomic on their last pass
   double max_cta_cost = 0, mean_cta_cost = 0;
 };
 

@@ -230,6 +230,16 @@ __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// fp32 reductions into C for split pieces (no return value: fire and forget at the L2)
+__device__ __forceinline__ void red_add_v4(float4* dst, const float4& v) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void red_add(float* dst, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (tcgen05): start address
 // >> 4 in [0,14), LBO = 1 in [16,30) (ignored for swizzled K-major), SBO = 1024
 // B >> 4 in [32,46) (8 rows x 128 B per swizzle atom), version 1 in [46,48),
@@ -299,7 +309,8 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   uint32_t* starts = reinterpret_cast<uint32_t*>(ctrl + 192);
   const uint32_t tables_u = ctrl_u + 256;
   const uint8_t* tables_s = ctrl + 256;
-  static_assert(256 + kMaxPanelStages * kTableBytes <= kSmemCtrlBytes, "control block too small");
+  static_assert(256 + kMaxPanelStages * kTableBytes <= kSmemStageOff, "control block too small");
+  static_assert(kSmemStageOff + 4 * 2048 <= kSmemCtrlBytes, "no room for the epilogue staging tiles");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -533,6 +544,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
     uint32_t acc_use[2] = {0, 0};
     int local = 0;
     const bool c_aligned = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+    float* stg = reinterpret_cast<float*>(ctrl + kSmemStageOff) + (warp - 2) * 512;   // 32 x 16 floats
     for (int it = it_begin; it < it_end; ++it, ++local) {
       const Item item = load_item(p, it);
       const SuperRow sr = p.srows[item.srow];
@@ -541,6 +553,8 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       // copy of the accumulator (TMEM columns master_col..) instead of writing C
       const bool fold_in = (item.count & kItemNotFirst) != 0;
       const bool to_master = (item.count & kItemNotLast) != 0;
+      const bool add_c = p.accumulate != 0;
+      const bool red_c = (item.count & kItemAtomic) != 0;   // a split piece: C += partial sums
       mbar_wait(bar_acc_full + 8 * as, acc_use[as] & 1, 5);
       const unsigned long long te0 = (tr && warp == 2 && lane == 0) ? sm_clock() : 0ull;
       ++acc_use[as];
@@ -570,27 +584,51 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             tmem_st16(t_acc + p.master_col + sg.tmem_col + c0, v);
             continue;
           }
-          if (jv) {
-            float* dst = cj + static_cast<int64_t>(sg.c_row0 + c0) * p.c_sr;
-            if (vec_ok && c0 + 16 <= sg.h) {
+          if (vec_ok && c0 + 16 <= sg.h) {
+            // Column-major C: a thread owns one column j, so its 16 values are 64 contiguous
+            // bytes but the warp's 32 columns are 32 different lines -- stored straight from the
+            // registers every st.v4 costs 32 LSU wavefronts (the first traces: 23 k cycles to
+            // drain 512 accumulator columns).  Transposed through a 2 KB per-warp staging tile
+            // (XOR-swizzled, conflict-free both ways) 4 lanes cover a column's 64 bytes and one
+            // instruction touches 8 lines instead of 32.
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                       __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-                float4* d4 = reinterpret_cast<float4*>(dst) + g;
-                if (p.accumulate) {
-                  const float4 old = *d4;
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (g ^ ((lane >> 1) & 3))) =
+                  make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                              __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            __syncwarp();
+            const int gl = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int jj = 8 * i + (lane >> 2);
+              float4 o = *reinterpret_cast<const float4*>(stg + jj * 16 + 4 * (gl ^ ((jj >> 1) & 3)));
+              const int jcol = j - lane + jj;
+              if (jcol < p.n) {
+                float4* d4 = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(jcol) * p.c_sj +
+                                                       (sg.c_row0 + c0 + 4 * gl));
+                if (red_c) {
+                  red_add_v4(d4, o);
+                } else {
+                  if (add_c) {
+                    const float4 old = *d4;
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *d4 = o;
                 }
-                *d4 = o;
               }
-            } else {
+            }
+            __syncwarp();
+          } else if (jv) {
+            float* dst = cj + static_cast<int64_t>(sg.c_row0 + c0) * p.c_sr;
 #pragma unroll
-              for (int r = 0; r < 16; ++r) {
-                if (c0 + r < sg.h) {
-                  float o = __uint_as_float(v[r]);
-                  float* d = dst + static_cast<int64_t>(r) * p.c_sr;
-                  if (p.accumulate) o += *d;
+            for (int r = 0; r < 16; ++r) {
+              if (c0 + r < sg.h) {
+                float o = __uint_as_float(v[r]);
+                float* d = dst + static_cast<int64_t>(r) * p.c_sr;
+                if (red_c) {
+                  red_add(d, o);
+                } else {
+                  if (add_c) o += *d;
                   *d = o;
                 }
               }
@@ -624,6 +662,34 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
                    : "memory");
     }
   }
+}
+
+// ------------------------------------------------------------------ zeroing of split tiles
+// One block per job: the rows of the job's super-row x `tile` columns of C.  Rows of a segment
+// are contiguous when C is column-major (c_sr == 1), columns when it is row-major (c_sj == 1);
+// threads run along whichever is contiguous.
+__global__ void zero_c_tiles_kernel(const ZeroJob* __restrict__ jobs, const SuperRow* __restrict__ srows,
+                                    const Segment* __restrict__ segs, float* __restrict__ C,
+                                    int64_t c_sr, int64_t c_sj, int n, int tile) {
+  const ZeroJob job = jobs[blockIdx.x];
+  const SuperRow sr = srows[job.srow];
+  const int jn = min(tile, n - job.j0);
+  for (int sidx = 0; sidx < sr.seg_count; ++sidx) {
+    const Segment sg = segs[sr.seg_begin + sidx];
+    const int total = sg.h * jn;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      int r, j;
+      if (c_sr == 1) { r = i % sg.h; j = i / sg.h; } else { j = i % jn; r = i / jn; }
+      C[static_cast<int64_t>(sg.c_row0 + r) * c_sr + static_cast<int64_t>(job.j0 + j) * c_sj] = 0.0f;
+    }
+  }
+}
+
+cudaError_t zero_c_tiles_launch(const SpmmParams& p, const ZeroJob* jobs, int n_jobs, cudaStream_t stream) {
+  if (n_jobs <= 0) return cudaSuccess;
+  zero_c_tiles_kernel<<<n_jobs, 512, 0, stream>>>(jobs, p.srows, p.segs, p.C, p.c_sr, p.c_sj, p.n,
+                                                   p.pair ? 2 * kTileJ : kTileJ);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ launch

@@ -37,7 +37,8 @@ struct SpmmParams {
 
 constexpr int kSpmmThreads   = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int kMaxPanelStages = 8;
-constexpr int kSmemCtrlBytes = 3072;  // barriers + per-stage run tables at the end
+constexpr int kSmemStageOff  = 3072;  // offset of the epilogue warps' staging tiles in the control block
+constexpr int kSmemCtrlBytes = 3072 + 4 * 2048;  // barriers + per-stage run tables + 4 staging tiles
 constexpr int kSmemMax       = 232448; // 227 KB opt-in limit per CTA
 
 // Bytes of dynamic shared memory for a configuration (includes 1 KB slack used
@@ -52,5 +53,9 @@ static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes) {
 cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
                         int64_t ldk, int precision, int grid, cudaStream_t stream,
                         const char** err);
+
+// Zeroes the C tiles that split pieces (kItemAtomic) accumulate into: the rows of each job's
+// super-row, columns [j0, j0 + tile).  Uses p.srows / p.segs / p.C / strides / n / pair.
+cudaError_t zero_c_tiles_launch(const SpmmParams& p, const ZeroJob* jobs, int n_jobs, cudaStream_t stream);
 
 }  // namespace sparta

@@ -28,7 +28,7 @@ class Options(C.Structure):
         ("seg_rows", C.c_int32), ("acc_cols", C.c_int32), ("panel_stages", C.c_int32),
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
         ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
-        ("max_chain", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("max_chain", C.c_int32), ("split_k", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -40,7 +40,8 @@ class Stats(C.Structure):
         ("a_packed_bytes", C.c_int64), ("b_bytes", C.c_int64), ("c_bytes", C.c_int64),
         ("grid", C.c_int32), ("smem_bytes", C.c_int32), ("sched_imbalance", C.c_double),
         ("upload_ms", C.c_double), ("kernel_launches", C.c_int64),
-        ("team", C.c_int32), ("cta_pair", C.c_int32),
+        ("team", C.c_int32), ("cta_pair", C.c_int32), ("split_pieces", C.c_int32), ("zero_tiles", C.c_int32),
+        ("sched_max_cycles", C.c_double),
     ]
 
     def as_dict(self):
@@ -58,6 +59,8 @@ SIGNATURES = {
     "sparta_device_count": (C.c_int, []),
     "sparta_vbr_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                     _vp, _vp, _vp, _vp, C.POINTER(Options)]),
+    "sparta_vbr_create_BA": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                       _vp, _vp, _vp, _vp, C.POINTER(Options)]),
     "sparta_bellpack_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, _vp, _vp, C.POINTER(Options)]),
     "sparta_csr_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, _vp, _vp, _vp,
@@ -77,6 +80,9 @@ SIGNATURES = {
     "sparta_vbr_spmm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
                                   _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
                                   C.POINTER(C.c_float)]),
+    "sparta_vbr_spmm_BA": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
+                                     _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
+                                     C.POINTER(C.c_float)]),
     "sparta_bellpack_spmm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp,
                                        _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
                                        C.POINTER(C.c_float)]),
@@ -100,6 +106,8 @@ SIGNATURES = {
     "sparta_host_bellpack_free": (C.c_int, [_vp]),
     "sparta_vbr_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          _vp, _vp, _vp, C.c_int64, C.POINTER(Options)]),
+    "sparta_vbr_plan_create_BA": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                            _vp, _vp, _vp, C.c_int64, C.POINTER(Options)]),
     "sparta_plan_array": (C.c_int, [_vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int32)]),
     "sparta_plan_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
@@ -181,6 +189,19 @@ class Handle:
         _check(lib.sparta_vbr_create(C.byref(h), rows, cols, len(nzcount), block_col_size,
                                      _ptr(row_part), _ptr(nzcount), _ptr(jab), _ptr(mab),
                                      C.byref(o)))
+        return cls(h, None)
+
+    @classmethod
+    def from_vbr_BA(cls, rows, cols, block_col_size, row_part, nzcount, jab, mab, **opts):
+        """The inverted product C = B*A (-M 6): B is [rows][n], C is [cols][n] (row-major views of
+        the reference's column-major n x rows and n x cols arrays)."""
+        lib = load()
+        row_part, nzcount, jab, mab = _i64(row_part), _i64(nzcount), _i64(jab), _f32(mab)
+        o = make_options(**opts)
+        h = _vp()
+        _check(lib.sparta_vbr_create_BA(C.byref(h), rows, cols, len(nzcount), block_col_size,
+                                        _ptr(row_part), _ptr(nzcount), _ptr(jab), _ptr(mab),
+                                        C.byref(o)))
         return cls(h, None)
 
     @classmethod
@@ -280,21 +301,24 @@ CHUNK_DT = np.dtype([("k0", "<i4"), ("mask", "<u4"), ("a_off16", "<u4"), ("a_byt
                      ("ksteps", "<i4"), ("tbl_bytes", "<u4"), ("tbl_off16", "<u4"),
                      ("pad", "<i4")])
 ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4"), ("chunk_off", "<i4"), ("count", "<u4")])
-ITEM_NOT_FIRST, ITEM_NOT_LAST, ITEM_COUNT_MASK = 1 << 31, 1 << 30, (1 << 30) - 1
+ITEM_NOT_FIRST, ITEM_NOT_LAST, ITEM_ATOMIC, ITEM_COUNT_MASK = 1 << 31, 1 << 30, 1 << 29, (1 << 29) - 1
 JOB_DT = np.dtype([("src_base", "<i8"), ("src_rs", "<i8"), ("src_ks", "<i8"), ("h", "<i4"),
                    ("h_pad", "<i4"), ("k_lo", "<i4"), ("k_w", "<i4"), ("dst_off16", "<u4"),
                    ("pad", "<i4", (3,))])
-_PLAN_DTYPES = [SEG_DT, SROW_DT, CHUNK_DT, ITEM_DT, np.dtype("<i4"), np.dtype("<i4"), JOB_DT, np.dtype("<u4")]
-_PLAN_NAMES = ["segs", "srows", "chunks", "items", "cta_ptr", "cta_items", "jobs", "tables"]
+ZERO_DT = np.dtype([("srow", "<i4"), ("j0", "<i4")])
+_PLAN_DTYPES = [SEG_DT, SROW_DT, CHUNK_DT, ITEM_DT, np.dtype("<i4"), np.dtype("<i4"), JOB_DT, np.dtype("<u4"), ZERO_DT]
+_PLAN_NAMES = ["segs", "srows", "chunks", "items", "cta_ptr", "cta_items", "jobs", "tables", "zero_jobs"]
 
 
-def vbr_plan(rows, cols, block_col_size, row_part, nzcount, jab, n, **opts):
-    """Host-only: the tile schedule the kernel would walk, as numpy record arrays."""
+def vbr_plan(rows, cols, block_col_size, row_part, nzcount, jab, n, transposed=False, **opts):
+    """Host-only: the tile schedule the kernel would walk, as numpy record arrays.
+    transposed: the schedule of the inverted product C = B*A (Handle.from_vbr_BA)."""
     lib = load()
     row_part, nzcount, jab = _i64(row_part), _i64(nzcount), _i64(jab)
     o = make_options(**opts)
     p = _vp()
-    _check(lib.sparta_vbr_plan_create(C.byref(p), rows, cols, len(nzcount), block_col_size,
+    create = lib.sparta_vbr_plan_create_BA if transposed else lib.sparta_vbr_plan_create
+    _check(create(C.byref(p), rows, cols, len(nzcount), block_col_size,
                                       _ptr(row_part), _ptr(nzcount), _ptr(jab), n, C.byref(o)))
     try:
         out = {}

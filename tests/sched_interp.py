@@ -62,7 +62,19 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
     Cm = np.full((n, rows), np.nan, dtype=np.float32)
     visited = np.zeros(len(items), dtype=bool)
     assert len(plan["cta_ptr"]) - 1 == plan["stats"]["grid"] // nshare
-    NOT_FIRST, NOT_LAST, COUNT = 1 << 31, 1 << 30, (1 << 30) - 1
+    NOT_FIRST, NOT_LAST, ATOMIC, COUNT = 1 << 31, 1 << 30, 1 << 29, (1 << 29) - 1
+    tile = 128 * nshare
+    # zero_c_tiles_kernel: the tiles split pieces add into start from zero
+    zeroed = set()
+    for job in plan["zero_jobs"]:
+        key = (int(job["srow"]), int(job["j0"]))
+        assert key not in zeroed
+        zeroed.add(key)
+        sr = srows[key[0]]
+        for sg in segs[sr["seg_begin"]:sr["seg_begin"] + sr["seg_count"]]:
+            Cm[key[1]:key[1] + tile, sg["c_row0"]:sg["c_row0"] + sg["h"]] = 0.0
+    covered = {}       # (srow, j0) -> [(first chunk, chunks)] over all pieces
+    n_atomic = 0
     for worker in range(len(plan["cta_ptr"]) - 1):
         master = {}        # per pair rank: the master accumulators of the (super-row, tile) in flight
         open_pass = None   # (srow, j0, next chunk) while a multi-pass item is in flight
@@ -75,14 +87,25 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
             tcols = [int(c) for c in sg_all["tmem_col"]] + [int(sr["n_cols"])]
             cnt, off = int(item["count"]) & COUNT, int(item["chunk_off"])
             fold_in, to_master = bool(int(item["count"]) & NOT_FIRST), bool(int(item["count"]) & NOT_LAST)
-            # passes of one (super-row, tile) run back to back on one worker, in chunk order
+            atomic = bool(int(item["count"]) & ATOMIC)
+            key = (int(item["srow"]), int(item["j0"]))
+            covered.setdefault(key, []).append((off, cnt))
+            assert key[1] % tile == 0 and (cnt > 0 or int(sr["chunk_count"]) == 0)
+            # passes of one piece run back to back on one worker, in chunk order
             if fold_in:
-                assert open_pass == (int(item["srow"]), int(item["j0"]), off)
+                assert open_pass == (key[0], key[1], off)
             else:
-                assert open_pass is None and off == 0
-            open_pass = (int(item["srow"]), int(item["j0"]), off + cnt) if to_master else None
+                assert open_pass is None
+                piece_start = off
+            open_pass = (key[0], key[1], off + cnt) if to_master else None
+            assert not (atomic and to_master), "only the last pass of a piece writes C"
             if not to_master:
-                assert off + cnt == int(sr["chunk_count"])
+                whole = piece_start == 0 and off + cnt == int(sr["chunk_count"])
+                # a piece writes C with plain stores iff it is the whole chunk list of its tile
+                assert atomic != whole
+                if atomic:
+                    assert key in zeroed
+                    n_atomic += 1
             if fold_in or to_master:   # working + master accumulators must both fit in TMEM
                 assert int(sr["n_cols"]) <= 256
             for cta in range(nshare):      # each CTA of a pair owns 128 of the item's columns
@@ -127,8 +150,21 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
                     master[cta] = acc
                     continue
                 for sg in sg_all:
-                    Cm[j0:j0 + jj, sg["c_row0"]:sg["c_row0"] + sg["h"]] = \
-                        acc[:jj, sg["tmem_col"]:sg["tmem_col"] + sg["h"]]
+                    part = acc[:jj, sg["tmem_col"]:sg["tmem_col"] + sg["h"]]
+                    if atomic:
+                        Cm[j0:j0 + jj, sg["c_row0"]:sg["c_row0"] + sg["h"]] += part
+                    else:
+                        Cm[j0:j0 + jj, sg["c_row0"]:sg["c_row0"] + sg["h"]] = part
         assert open_pass is None
     assert visited.all()
+    # every (super-row, column tile): its pieces tile the chunk list exactly once
+    n_tiles = (n + tile - 1) // tile
+    assert len(covered) == len(srows) * n_tiles
+    for (s_id, _), ranges in covered.items():
+        pos = 0
+        for off, cnt in sorted(ranges):
+            assert off == pos
+            pos += cnt
+        assert pos == int(srows[s_id]["chunk_count"])
+    assert n_atomic == plan["stats"]["split_pieces"] and len(zeroed) == plan["stats"]["zero_tiles"]
     return Cm

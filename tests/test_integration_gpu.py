@@ -16,6 +16,8 @@ HEADER = "matrix,rows,cols,nonzeros"
     ["-M", "2", "-a", "5", "-b", "16", "-B", "16", "-t", "0.6"],                 # cuSPARSE CSR SpMM -> sm_100a CSR kernel
     ["-M", "4", "-a", "5", "-b", "16", "-B", "16", "-t", "0.6"],                 # cuBLAS VBR loop -> sm_100a VBR
     ["-M", "7", "-a", "5", "-b", "16", "-B", "16", "-t", "0.6"],                 # batched SGEMM -> tf32
+    ["-M", "6", "-a", "5", "-b", "16", "-B", "16", "-t", "0.6"],                 # inverted product C = B*A
+    ["-M", "11", "-a", "5", "-b", "16", "-B", "16", "-t", "0.6"],                # CUTLASS inverted product
     ["-M", "3", "-a", "2", "-b", "16", "-B", "16", "-F", "1"],                   # cuSPARSE Blocked-ELL
     ["-M", "8", "-a", "5", "-b", "16", "-B", "16", "-t", "0.6", "-F", "1"],      # CUTLASS EllGemm
     ["-M", "10", "-a", "3", "-b", "16", "-B", "16", "-t", "0.3", "-F", "1"],     # CUTLASS per-block loop
@@ -45,9 +47,10 @@ def test_reference_cli_runs_on_our_library(tmp_path, flags, lib):
 
 
 def test_reference_cli_out_of_scope_mode_exits_loudly(tmp_path, lib):
+    """-M 12 (batched inverted product) is not provided: the shim must say so and exit non-zero."""
     if not os.path.exists(BIN):
         pytest.skip("integration/_ref/cuda_multiply_b200 was not prebuilt")
-    res = subprocess.run([BIN, "-f", os.path.join(ROOT, "tests", "golden", "rmat8.el"), "-P", "1", "-M", "6", "-b", "16",
+    res = subprocess.run([BIN, "-f", os.path.join(ROOT, "tests", "golden", "rmat8.el"), "-P", "1", "-M", "12", "-b", "16",
                           "-B", "16", "-a", "5", "-c", "32", "-v", "0", "-o", str(tmp_path / "x.csv")],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode != 0 and "not provided" in res.stderr

@@ -123,3 +123,79 @@ def test_unbounded_chain_keeps_wide_super_rows(lib):
     c = sparta_b200.vbr_plan(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], 256, precision="tf32")
     assert a["srows"]["n_cols"].max() == 512 and b["srows"]["n_cols"].max() == 512
     assert c["srows"]["n_cols"].max() == 256 and len(c["items"]) > len(c["srows"])
+
+
+@pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
+@pytest.mark.parametrize("precision,esize,max_chain", [("bf16", 2, 0), ("tf32", 4, 24)])
+def test_split_pieces_cover_every_chunk_once(oracle, lib, precision, esize, max_chain, pair):
+    """split_k = 2: the chunk lists are cut into one piece per worker; the interpreter checks that
+    the pieces of every (super-row, tile) tile its chunk list, that only whole lists use plain
+    stores, that every tile a piece adds into is zeroed first, and that the product is unchanged."""
+    rng = np.random.default_rng(31)
+    heights = [64, 64, 64, 30, 64, 64, 64, 64, 64, 17, 64, 64]
+    v = random_vbr(rng, len(heights), 4096, 64, heights, 0.7, values="int")
+    n = 300
+    Bm = rng.integers(-3, 4, size=(n, 4096)).astype(np.float32)
+    plan = sparta_b200.vbr_plan(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], n,
+                                precision=precision, cta_pair=pair, max_chain=max_chain, split_k=2, num_ctas=20)
+    st = plan["stats"]
+    assert st["split_pieces"] > 0 and st["zero_tiles"] > 0
+    assert st["sched_imbalance"] < 1.6   # forced on a tiny case: pieces have a minimum length
+    atomic = (plan["items"]["count"] & sparta_b200.lib.ITEM_ATOMIC) != 0
+    assert atomic.sum() == st["split_pieces"]
+    if max_chain:
+        for it in plan["items"]:
+            c0 = plan["srows"][it["srow"]]["chunk_begin"] + it["chunk_off"]
+            cnt = int(it["count"]) & sparta_b200.lib.ITEM_COUNT_MASK
+            assert int(plan["chunks"]["ksteps"][c0:c0 + cnt].sum()) <= max_chain
+    Cm = sched_interp.run_plan(plan, v["mab"], Bm, 4096, n, v["rows"], esize=esize)
+    assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
+
+
+def test_split_is_chosen_only_when_it_pays(lib):
+    rng = np.random.default_rng(32)
+    # few heavy super-rows for many workers: whole units cannot fill the grid
+    v = random_vbr(rng, 24, 8192, 64, [64] * 24, 0.8, values="int")
+    few = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048)
+    never = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048, split_k=1)
+    assert few["stats"]["split_pieces"] > 0 and never["stats"]["split_pieces"] == 0
+    # whole units keep 24 of the 74 CTA pairs busy; the split plan fills the grid evenly
+    assert never["stats"]["grid"] == 48 and few["stats"]["grid"] == 148
+    assert few["stats"]["sched_imbalance"] < 1.25
+    # many units per worker: list scheduling is already balanced, nothing is split
+    v = random_vbr(rng, 400, 1024, 64, [64] * 400, 0.3, values="int")
+    many = sparta_b200.vbr_plan(v["rows"], 1024, 64, v["row_part"], v["nzcount"], v["jab"], 2048, num_ctas=16)
+    assert many["stats"]["split_pieces"] == 0 and many["stats"]["zero_tiles"] == 0
+
+
+BA_CASES = [
+    # block_rows, cols, w, heights, density, m (rows of B)
+    (6, 96, 16, [16] * 6, 0.5, 40),
+    (5, 70, 16, [3, 17, 1, 64, 30], 0.6, 130),      # ragged heights become ragged k extents; cols % w != 0
+    (4, 64, 3, [4, 3, 1, 1], 0.7, 2),
+    (3, 300, 100, [64, 64, 20], 0.8, 16),
+    (3, 64, 32, [200, 70, 9], 1.0, 8),              # tall block-rows: several K slabs per block
+]
+
+
+@pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
+@pytest.mark.parametrize("precision,esize", [("bf16", 2), ("tf32", 4)])
+@pytest.mark.parametrize("case", range(len(BA_CASES)))
+def test_inverted_product_plan_matches_oracle(oracle, lib, case, precision, esize, pair):
+    """C = B*A (-M 6): the schedule of the transposed operand, interpreted on the CPU, against the
+    oracle's restatement of the arithmetic cublas_blockmat_multiplyBA intends and against numpy."""
+    block_rows, cols, w, heights, density, m = BA_CASES[case]
+    rng = np.random.default_rng(300 + case)
+    v = random_vbr(rng, block_rows, cols, w, heights, density, values="int")
+    Bt = rng.integers(-3, 4, size=(v["rows"], m)).astype(np.float32)      # row k = column k of B
+    plan = sparta_b200.vbr_plan(v["rows"], cols, w, v["row_part"], v["nzcount"], v["jab"], m,
+                                transposed=True, precision=precision, cta_pair=pair)
+    st = plan["stats"]
+    assert st["rows"] == cols and st["nz_blocks"] == v["jab"].size
+    # the interpreter takes the dense operand as [n, K] with K = A's rows here
+    Cm = sched_interp.run_plan(plan, v["mab"], np.ascontiguousarray(Bt.T), v["rows"], m, cols, esize=esize)
+    Cref = oracle.vbr_multiply_BA(v, Bt, m)                                # [cols, m]
+    assert not np.isnan(Cm).any()
+    assert np.array_equal(Cm, Cref.T)
+    from tests.util import vbr_to_dense
+    assert np.array_equal(Cref, (Bt.T.astype(np.float64) @ vbr_to_dense(v)).T.astype(np.float32))

@@ -297,3 +297,138 @@ def test_tf32_long_positive_sums_within_1e5(lib):
     Cu = gpu_multiply(v, Bm, n, "tf32", max_chain=-1)
     assert rel_err(Cu, ref) >= rel_err(Cg, ref)
     assert rel_err(Cu, ref) <= TOL_UNROUNDED["tf32"]
+
+
+@pytest.mark.parametrize("mode", ["single", "pair"])
+@pytest.mark.parametrize("precision,max_chain", [("bf16", 0), ("fp16", 0), ("tf32", 24), ("tf32", 0)])
+def test_split_pieces_bit_exact(oracle, lib, precision, max_chain, mode):
+    """split_k = 2: the column-block lists are cut into one piece per worker and the pieces add
+    their partial sums to C with red.global.add.f32 after zero_c_tiles_kernel (sched_types.h).
+    Integer operands: exact whatever the order of the additions.  Launching again must give the
+    same C (the tiles are re-zeroed before every launch)."""
+    rng = np.random.default_rng(41)
+    heights = [64, 64, 64, 30, 64, 64, 64, 64, 64, 17, 64, 64, 1, 64]
+    v = random_vbr(rng, len(heights), 4096, 64, heights, 0.7, values="int")
+    n = 300
+    Bm = rng.integers(-3, 4, size=(n, 4096)).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    precision=precision, max_chain=max_chain, split_k=2, **MODES[mode])
+    try:
+        h.set_B(Bm, 4096, n)
+        st = h.stats()
+        assert st["split_pieces"] > 0 and st["zero_tiles"] > 0
+        h.run()
+        a = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"]).copy()
+        h.run()
+        b = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"])
+    finally:
+        h.close()
+    assert np.array_equal(a, Cref) and np.array_equal(b, Cref)
+
+
+def test_split_pieces_accumulate_and_row_major(oracle, lib):
+    """Split pieces with beta = 1 (no zeroing: the pieces add onto the caller's C) and with the
+    Blocked-ELL path's row-major C."""
+    rng = np.random.default_rng(42)
+    v = random_vbr(rng, 10, 2048, 64, [64] * 10, 0.8, values="int")
+    n = 520
+    Bm = rng.integers(-3, 4, size=(n, 2048)).astype(np.float32)
+    C0 = rng.integers(-5, 6, size=(n, v["rows"])).astype(np.float32)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 2048, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    accumulate=1, split_k=2)
+    h.set_B(Bm, 2048, n)
+    h.set_C(C0, v["rows"])
+    assert h.stats()["split_pieces"] > 0
+    h.run()
+    out = h.get_C(np.zeros_like(C0), v["rows"])
+    h.close()
+    assert np.array_equal(out, oracle.vbr_multiply(v, Bm, n, C_init=C0))
+    # row-major B and C (b_layout = c_layout = 2)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 2048, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    split_k=2, b_layout=2, c_layout=2)
+    B_rm = np.ascontiguousarray(Bm.T)
+    h.set_B(B_rm, n, n)
+    assert h.stats()["split_pieces"] > 0
+    h.run()
+    out = h.get_C(np.zeros((v["rows"], n), np.float32), n)
+    h.close()
+    assert np.array_equal(out, oracle.vbr_multiply(v, Bm, n).T)
+
+
+def test_split_real_operands_within_tolerance(oracle, lib):
+    rng = np.random.default_rng(43)
+    v = random_vbr(rng, 12, 4096, 64, [64] * 12, 0.9, values="uniform")
+    n = 256
+    Bm = rng.random((n, 4096), dtype=np.float32)
+    for precision in ("bf16", "tf32"):
+        Cg = gpu_multiply(v, Bm, n, precision, split_k=2)
+        C_rounded = oracle.vbr_multiply(rounded(v, precision), round_to(Bm, precision), n)
+        assert rel_err(Cg, C_rounded) <= TOL_ROUNDED
+        assert rel_err(Cg, oracle.vbr_multiply(v, Bm, n)) <= TOL_UNROUNDED[precision]
+
+
+BA_CASES = [
+    (6, 96, 16, [16] * 6, 0.5, 40),
+    (5, 70, 16, [3, 17, 1, 64, 30], 0.6, 130),      # ragged heights = ragged k extents; cols % w != 0
+    (3, 300, 100, [64, 64, 20], 0.8, 16),
+    (3, 64, 32, [200, 70, 9], 1.0, 8),
+    (24, 1024, 64, [64] * 24, 0.5, 384),
+    (40, 2048, 64, [64] * 37 + [63, 30, 7], 0.5, 700),
+]
+
+
+@pytest.mark.parametrize("mode", ["single", "pair"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
+@pytest.mark.parametrize("case", range(len(BA_CASES)))
+def test_inverted_product_bit_exact(oracle, lib, case, precision, mode):
+    """C = B*A (-M 6 / -M 11 replacement, sparta_vbr_create_BA): integer operands, exact."""
+    block_rows, cols, w, heights, density, m = BA_CASES[case]
+    rng = np.random.default_rng(400 + case)
+    v = random_vbr(rng, block_rows, cols, w, heights, density, values="int")
+    Bt = rng.integers(-3, 4, size=(v["rows"], m)).astype(np.float32)      # row k = column k of B
+    h = sparta_b200.Handle.from_vbr_BA(v["rows"], cols, w, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                       precision=precision, **MODES[mode])
+    try:
+        h.set_B(Bt, m, m)
+        st = h.stats()
+        assert st["rows"] == cols and st["nztot"] == v["mab"].size
+        h.run()
+        out = h.get_C(np.zeros((cols, m), np.float32), m)
+    finally:
+        h.close()
+    assert np.array_equal(out, oracle.vbr_multiply_BA(v, Bt, m))
+
+
+def test_inverted_product_one_shot_and_tolerance(oracle, lib):
+    from sparta_b200.api import vbr_spmm_BA
+    rng = np.random.default_rng(44)
+    heights = [64] * 9 + [30]
+    v = random_vbr(rng, len(heights), 640, 64, heights, 0.6, values="uniform")
+    m = 200
+    Bt = rng.random((v["rows"], m), dtype=np.float32)
+    A = VBR(v["rows"], v["cols"], 64, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+    for precision in ("bf16", "tf32"):
+        Cg, dt = vbr_spmm_BA(A, Bt, m, precision)
+        assert dt > 0
+        C_rounded = oracle.vbr_multiply_BA(rounded(v, precision), round_to(Bt, precision), m)
+        assert rel_err(Cg, C_rounded) <= TOL_ROUNDED
+        assert rel_err(Cg, oracle.vbr_multiply_BA(v, Bt, m)) <= TOL_UNROUNDED[precision]
+
+
+def test_inverted_product_column_block_shards(oracle, lib):
+    """Shards of the inverted product are ranges of column blocks: slabs of C's columns."""
+    rng = np.random.default_rng(45)
+    v = random_vbr(rng, 12, 512, 32, [32] * 12, 0.5, values="int")
+    m = 64
+    Bt = rng.integers(-2, 3, size=(v["rows"], m)).astype(np.float32)
+    Cref = oracle.vbr_multiply_BA(v, Bt, m)
+    slabs = []
+    for lo, hi in ((0, 5), (5, 11), (11, 16)):
+        h = sparta_b200.Handle.from_vbr_BA(v["rows"], 512, 32, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                           block_row_begin=lo, block_row_end=hi)
+        h.set_B(Bt, m, m)
+        h.run()
+        slabs.append(h.get_C(np.zeros(((hi - lo) * 32, m), np.float32), m))
+        h.close()
+    assert np.array_equal(np.concatenate(slabs, axis=0), Cref)
