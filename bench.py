@@ -257,7 +257,7 @@ def workload_config(args, wl, v):
             "block_col_size": wl["w"], "block_rows": int(v["block_rows"]), "nz_blocks": int(len(v["jab"])),
             "nztot": int(v["nztot"]), "B_cols": wl["n"], "flop_per_step": 2.0 * v["nztot"] * wl["n"],
             "l2_policy": "inputs larger than L2 (packed A alone exceeds 126 MB); no flush",
-            "parallelism": f"row-block shards x{args.gpus}, B replicated by one NCCL broadcast"}
+            "parallelism": f"row-block shards x{args.gpus} ({args.partition}-balanced), B replicated by one NCCL broadcast"}
 
 
 def read_peaks():
@@ -317,7 +317,13 @@ def run_ours(args, wl):
     v = build_vbr(wl, N, rowptr, colind, grouping)
     t_fill = time.perf_counter() - t0
     n = wl["n"]
-    cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
+    if args.partition == "model":
+        # contiguous block-row ranges balanced on the scheduler's modelled kernel time per shard
+        cuts = sparta_b200.partition_block_rows_modelled(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"],
+                                                         v["jab"], n, world, precision=args.precision,
+                                                         **tuning_opts(args))
+    else:
+        cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
     lo, hi = int(cuts[rank]), int(cuts[rank + 1])
     if rank == 0:
         log(f"[bench] matrix {N}x{N} nnz={len(colind)} gen {t_gen:.1f}s blocking {t_block:.1f}s fill {t_fill:.1f}s "
@@ -422,6 +428,7 @@ def run_ours(args, wl):
             "setup": {"blocking_s": t_block, "vbr_fill_s": t_fill, "matrix_gen_s": t_gen,
                       "a_upload_pack_ms": st["upload_ms"], "b_broadcast_s": t_bcast,
                       "sched_imbalance": st["sched_imbalance"], "grid": st["grid"], "items": st["items"],
+                      "team": st["team"], "split_pieces": st["split_pieces"], "zero_tiles": st["zero_tiles"],
                       "shard_block_rows": [int(c) for c in cuts]},
         }
         print(json.dumps(line), flush=True)
@@ -431,7 +438,7 @@ def run_ours(args, wl):
 
 def tuning_opts(args):
     o = {}
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k"):
         val = getattr(args, k)
         if val:
             o[k] = val
@@ -569,7 +576,9 @@ def main():
     ap.add_argument("--cpu-gflop-per-step", type=float, default=8.0,
                     help="--impl reference: nonzero-block GFLOP per thread-step sample")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain"):
+    ap.add_argument("--partition", default="model", choices=["model", "area"],
+                    help="multi-GPU block-row partition: balanced on modelled shard time (default) or on nonzero-block area")
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k"):
         ap.add_argument("--" + k.replace("_", "-"), dest=k, type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -59,7 +59,7 @@ typedef struct sparta_options {
   int64_t block_row_end;   /* shard: one past the last block-row (default: all) */
   int32_t cta_pair;      /* 0/2: CTA pairs, tcgen05 cta_group::2, 256-column tiles (default); 1: single CTAs */
   int32_t row_order;     /* 0/2: super-rows group block-rows of similar block count (default); 1: input order */
-  int32_t l2_slab_mb;    /* B columns kept L2-resident per pass, in MiB of B (default 80) */
+  int32_t l2_slab_mb;    /* B columns walked per pass over A, in MiB of B (default 160) */
   int32_t max_chain;     /* longest run of tcgen05.mma accumulations into one TMEM accumulator before the
                             partial sum is drained and added to C in fp32 by the epilogue; 0 = the
                             precision's default (tf32: 128, bf16/fp16: unlimited), -1 = unlimited */
@@ -149,7 +149,8 @@ int sparta_csr_create(sparta_handle** out, int64_t rows, int64_t cols, const int
  * handle's device (e.g. the target of an NCCL broadcast). */
 int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device);
 
-/* Optional: initial C for accumulate = 1 (same layout/ld rules as sparta_get_C). */
+/* Initial C for handles created with accumulate = 1 (same layout/ld rules as sparta_get_C);
+ * SPARTA_ERR_STATE on an accumulate = 0 handle, whose C is defined by the multiply alone. */
 int sparta_set_C(sparta_handle* h, const float* C, int64_t ld, int on_device);
 
 /* One multiply on the handle's stream.  *dt_ms (may be NULL) = CUDA-event time
@@ -169,6 +170,16 @@ int sparta_run_traced(sparta_handle* h, int32_t worker, uint64_t* records, int64
 
 /* Copy the result (rows x n fp32) out.  on_device != 0: C is a device pointer. */
 int sparta_get_C(sparta_handle* h, float* C, int64_t ld, int on_device);
+
+/* The result with its rows back in the ORIGINAL order: row r of the handle's C (blocked order,
+ * vbr.cpp:355) is written to row row_map[r] of C, row_map = the reference's get_permutation
+ * (src/general/utilities.cpp:8-20, sparta_host_permutation) restricted to the handle's rows.  C
+ * has out_rows rows in the handle's C layout.  The reference leaves C in blocked order
+ * (SURVEY.md 8a quirk 2); this is the un-permuting read-back of 8(f)-4.  on_device != 0: C is a
+ * device buffer and only the mapped rows are written -- ranks of a multi-GPU run can scatter
+ * their slabs straight into one full-size matrix.  Host C: unmapped rows come back as zeros. */
+int sparta_get_C_permuted(sparta_handle* h, float* C, int64_t ld, const int64_t* row_map,
+                          int64_t out_rows, int on_device);
 
 /* Raw device views for zero-copy consumers (valid until the next set_B / destroy). */
 void* sparta_C_device_ptr(sparta_handle* h);
@@ -223,6 +234,15 @@ int sparta_release_workspace(void);
 /* Contiguous block-row ranges balanced on nonzero-block area; cuts[parts+1]. */
 int sparta_partition_block_rows(int64_t block_rows, const int64_t* row_part,
                                 const int64_t* nzcount, int32_t parts, int64_t* cuts);
+
+/* The same kind of partition balanced on the MODELLED kernel time of every shard (the tile
+ * scheduler's cost model: bytes staged per chunk, drain per work item) rather than on area: sparse
+ * block-rows cost more per FLOP than dense ones.  n = columns of B, opt = the options the handles
+ * will be created with (NULL for defaults). */
+int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t block_rows,
+                                         int64_t block_col_size, const int64_t* row_part,
+                                         const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                         const sparta_options* opt, int32_t parts, int64_t* cuts);
 
 /* ---- host-side format builders (no GPU needed; bit-exact with the reference) ---- */
 

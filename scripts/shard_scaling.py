@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--opts", default="", help="extra handle options, e.g. num_ctas=144,l2_slab_mb=160")
+    ap.add_argument("--partition", default="area", choices=["area", "model"])
     args = ap.parse_args()
     import torch
     wl = bench.WORKLOADS[args.workload]
@@ -36,16 +38,22 @@ def main():
     from sparta_b200 import synth
     Bd = torch.from_numpy(synth.seeded_B(v["cols"], n, seed=2)).cuda()
     total_flops = 2.0 * v["nztot"] * n
+    extra = {k: int(x) for k, x in (kv.split("=") for kv in args.opts.split(",") if kv)}
     results = []
     for split in [int(x) for x in args.split.split(",")]:
         t1 = None
         for world in [int(x) for x in args.worlds.split(",")]:
-            cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
+            if args.partition == "model":
+                cuts = sparta_b200.partition_block_rows_modelled(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"],
+                                                                 v["jab"], n, world, precision=args.precision,
+                                                                 split_k=split, **extra)
+            else:
+                cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
             per_rank = []
             for r in range(world):
                 h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
                                                 v["mab"], precision=args.precision, block_row_begin=int(cuts[r]),
-                                                block_row_end=int(cuts[r + 1]), split_k=split)
+                                                block_row_end=int(cuts[r + 1]), split_k=split, **extra)
                 h.set_B_device(Bd.data_ptr(), v["cols"], n)
                 st = h.stats()
                 stream = torch.cuda.ExternalStream(h.stream)

@@ -110,6 +110,8 @@ struct sparta_handle {
   int32_t* d_cta_ptr = nullptr;
   int32_t* d_cta_items = nullptr;
   ZeroJob* d_zero_jobs = nullptr;
+  unsigned long long* d_sync = nullptr;   // grid-wide counter of the in-kernel zeroing (SpmmParams)
+  unsigned long long sync_total = 0;      // CTAs that have bumped it over all launches so far
   // CSR handles
   int64_t* d_rowptr = nullptr;
   int32_t* d_colind = nullptr;
@@ -133,7 +135,7 @@ static void resolve_options(const sparta_options* in, sparta_options* o) {
   }
   if (o->seg_rows == 0) o->seg_rows = 64;
   if (o->acc_cols == 0) o->acc_cols = 512;
-  if (o->l2_slab_mb <= 0) o->l2_slab_mb = 80;
+  if (o->l2_slab_mb <= 0) o->l2_slab_mb = 160;
   if (o->panel_stages == 0) o->panel_stages = 5;
 }
 
@@ -279,7 +281,7 @@ static void free_handle(sparta_handle* h) {
   cudaStream_t s = h->stream;
   if (s) {
     dev_free(h->d_segs, s); dev_free(h->d_srows, s); dev_free(h->d_chunks, s); dev_free(h->d_tables, s);
-    dev_free(h->d_a, s); dev_free(h->d_items, s); dev_free(h->d_cta_ptr, s); dev_free(h->d_cta_items, s); dev_free(h->d_zero_jobs, s);
+    dev_free(h->d_a, s); dev_free(h->d_items, s); dev_free(h->d_cta_ptr, s); dev_free(h->d_cta_items, s); dev_free(h->d_zero_jobs, s); dev_free(h->d_sync, s);
     dev_free(h->d_rowptr, s); dev_free(h->d_colind, s); dev_free(h->d_val, s); dev_free(h->d_row_order, s);
     dev_free(h->d_B, s); dev_free(h->d_C, s);
     cudaStreamSynchronize(s);   // the blocks are back in the pool before the stream goes away
@@ -730,10 +732,56 @@ static int copy_c(sparta_handle* h, float* C, int64_t ld, int on_device, bool to
 }
 
 int sparta_set_C(sparta_handle* h, const float* C, int64_t ld, int on_device) {
+  // with accumulate = 0 the multiply overwrites C, except the rows of empty block-rows, which
+  // rely on C's initial zero fill (build_assignment): an initial C only makes sense for beta = 1
+  if (h && !h->accumulate) return fail(SPARTA_ERR_STATE, "sparta_set_C needs a handle created with accumulate = 1");
   return copy_c(h, const_cast<float*>(C), ld, on_device, true);
 }
 int sparta_get_C(sparta_handle* h, float* C, int64_t ld, int on_device) {
   return copy_c(h, C, ld, on_device, false);
+}
+
+// C with its rows moved to row_map[r]: the scatter runs on the device (HBM-bound, 2 x C bytes).
+int sparta_get_C_permuted(sparta_handle* h, float* C, int64_t ld, const int64_t* row_map, int64_t out_rows,
+                          int on_device) {
+  if (!h || !C || !row_map) return fail(SPARTA_ERR_INVALID, "NULL handle, C or row_map");
+  if (h->n == 0) return fail(SPARTA_ERR_STATE, "set_B must be called first");
+  const int64_t rows = h->rows, n = h->n;
+  if (out_rows < rows) return fail(SPARTA_ERR_INVALID, "out_rows smaller than the handle's rows");
+  const int64_t width = h->c_row_major ? n : out_rows;
+  if (ld < width) return fail(SPARTA_ERR_INVALID, "leading dimension of C too small");
+  for (int64_t r = 0; r < rows; ++r)
+    if (row_map[r] < 0 || row_map[r] >= out_rows) return fail(SPARTA_ERR_INVALID, "row_map entry out of range");
+  if (rows == 0 || n == 0) return SPARTA_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  int64_t* d_map = nullptr;
+  float* d_tmp = nullptr;
+  CU_TRY(dev_alloc(&d_map, static_cast<size_t>(rows) * sizeof(int64_t), h->stream));
+  cudaError_t e = cudaMemcpyAsync(d_map, row_map, static_cast<size_t>(rows) * sizeof(int64_t),
+                                  cudaMemcpyHostToDevice, h->stream);
+  const int64_t lines = h->c_row_major ? out_rows : n;
+  float* dst = C;
+  int64_t dst_ld = ld;
+  if (e == cudaSuccess && !on_device) {
+    // host destination: scatter into a compact device image of the whole output first (rows no
+    // block-row of this handle maps to come back as zeros)
+    dst_ld = width;
+    const size_t bytes = static_cast<size_t>(lines) * width * sizeof(float);
+    e = dev_alloc(&d_tmp, bytes, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_tmp, 0, bytes, h->stream);
+    dst = d_tmp;
+  }
+  if (e == cudaSuccess)
+    e = permute_rows(h->d_C, h->c_row_major ? h->ldc : 1, h->c_row_major ? 1 : h->ldc, dst,
+                     h->c_row_major ? dst_ld : 1, h->c_row_major ? 1 : dst_ld, d_map, rows, n, h->stream);
+  if (e == cudaSuccess && !on_device)
+    e = cudaMemcpy2DAsync(C, ld * sizeof(float), d_tmp, width * sizeof(float), width * sizeof(float), lines,
+                          cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  dev_free(d_map, h->stream);
+  dev_free(d_tmp, h->stream);
+  if (e != cudaSuccess) return fail_cuda(e, "permuted read-back of C");
+  return SPARTA_OK;
 }
 
 static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int trace_worker = 0,
@@ -783,12 +831,24 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   p.acc_stage_cols = h->st.acc_cols;
   const char* err = "";
   if (!h->as.zero_jobs.empty() && !h->accumulate) {
-    // split pieces add partial sums: their C tiles start from zero (C := A*B semantics)
-    const cudaError_t ez = zero_c_tiles_launch(p, h->d_zero_jobs, static_cast<int>(h->as.zero_jobs.size()), h->stream);
-    if (ez != cudaSuccess) return fail_cuda(ez, "zeroing the split C tiles");
+    // split pieces add partial sums: their C tiles start from zero (C := A*B semantics); the
+    // kernel zeroes them itself and every CTA of the grid reports in on the counter
+    if (!h->d_sync) {
+      CU_TRY(dev_alloc(&h->d_sync, sizeof(unsigned long long), h->stream));
+      CU_TRY(cudaMemsetAsync(h->d_sync, 0, sizeof(unsigned long long), h->stream));
+      h->sync_total = 0;
+    }
+    h->sync_total += static_cast<unsigned long long>(h->as.grid);
+    p.zero_jobs = h->d_zero_jobs;
+    p.n_zero_jobs = static_cast<int32_t>(h->as.zero_jobs.size());
+    p.sync_counter = h->d_sync;
+    p.sync_target = h->sync_total;
   }
   cudaError_t e = spmm_launch(p, h->d_B, h->cols, h->ldk, h->sopt.precision, h->as.grid, h->stream, &err);
-  if (e != cudaSuccess) return fail_cuda(e, err);
+  if (e != cudaSuccess) {
+    if (p.n_zero_jobs) h->sync_total -= static_cast<unsigned long long>(h->as.grid);   // nothing ran
+    return fail_cuda(e, err);
+  }
   ++h->launches;
   return SPARTA_OK;
 }
@@ -1001,6 +1061,80 @@ int sparta_release_workspace(void) {
   }
   cudaSetDevice(cur);
   cudaGetLastError();
+  return SPARTA_OK;
+}
+
+// Contiguous block-row ranges balanced on the MODELLED kernel time of each shard instead of its
+// nonzero-block area: sparse block-rows cost more per FLOP (a B panel is fetched per chunk however
+// few rows share it) and every work item pays a fixed drain, so equal areas are not equal times --
+// on the bench matrix the sparse tail shard of an area partition runs 1.3-1.4x longer than the
+// dense head.  Fixed point: start from the area partition; build every shard's schedule; spread
+// its modelled time (the slowest worker's cycles) over its block-rows in proportion to their
+// current weight; re-cut on the new weights; keep the best of a few rounds.
+int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t block_rows,
+                                         int64_t block_col_size, const int64_t* row_part,
+                                         const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                         const sparta_options* opt, int32_t parts, int64_t* cuts) {
+  if (block_rows < 0 || parts <= 0 || !cuts || cols <= 0 || block_col_size <= 0 || n <= 0 ||
+      (block_rows && (!row_part || !nzcount)))
+    return fail(SPARTA_ERR_INVALID, "invalid partition request");
+  (void)rows;
+  sparta_options o;
+  resolve_options(opt, &o);
+  ScheduleOptions so;
+  so.precision = o.precision;
+  so.seg_rows = o.seg_rows;
+  so.acc_cols = o.acc_cols;
+  so.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  so.pair = o.cta_pair != 1;
+  so.sort_rows = o.row_order != 1;
+  so.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
+  so.max_chain = o.max_chain;
+  so.split = o.split_k;
+  std::vector<double> weight(block_rows);
+  for (int64_t b = 0; b < block_rows; ++b)
+    weight[b] = 1.0 + static_cast<double>(nzcount[b]) * (row_part[b + 1] - row_part[b]);
+  std::vector<int64_t> cur(parts + 1), best(parts + 1);
+  double best_worst = -1;
+  for (int round = 0; round < 6; ++round) {
+    // cut on the prefix sums of the weights
+    std::vector<double> prefix(block_rows + 1, 0.0);
+    for (int64_t b = 0; b < block_rows; ++b) prefix[b + 1] = prefix[b] + weight[b];
+    cur[0] = 0;
+    for (int i = 1; i < parts; ++i) {
+      const double target = prefix[block_rows] * i / parts;
+      int64_t b = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
+      if (b > 0 && target - prefix[b - 1] < prefix[b] - target) --b;
+      cur[i] = std::min(std::max(b, cur[i - 1]), block_rows);
+    }
+    cur[parts] = block_rows;
+    // modelled time of every shard
+    std::vector<double> t(parts, 0.0);
+    double worst = 0;
+    for (int i = 0; i < parts; ++i) {
+      if (cur[i + 1] <= cur[i]) continue;
+      BlockRows br;
+      int64_t src_lo = 0, src_hi = 0;
+      const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, cur[i], cur[i + 1],
+                                         &br, &src_lo, &src_hi);
+      Structure st;
+      Assignment as;
+      if (!*e) e = build_structure(br, so, &st);
+      if (!*e) e = build_assignment(st, so, n, cols, &as);
+      if (*e) return fail(SPARTA_ERR_INVALID, e);
+      t[i] = as.max_cta_cost;
+      worst = std::max(worst, t[i]);
+    }
+    if (best_worst < 0 || worst < best_worst) { best_worst = worst; best = cur; }
+    for (int i = 0; i < parts; ++i) {
+      double wsum = 0;
+      for (int64_t b = cur[i]; b < cur[i + 1]; ++b) wsum += weight[b];
+      if (wsum <= 0 || t[i] <= 0) continue;
+      const double scale = t[i] / wsum;
+      for (int64_t b = cur[i]; b < cur[i + 1]; ++b) weight[b] *= scale;
+    }
+  }
+  for (int i = 0; i <= parts; ++i) cuts[i] = best[i];
   return SPARTA_OK;
 }
 

@@ -153,4 +153,32 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
   return cudaGetLastError();
 }
 
+// HBM-bound scatter of C's rows: 2 x rows x n x 4 bytes.  Threads run along whichever dimension is
+// contiguous in the source so the reads coalesce; the writes are 4-byte scatters when C is
+// column-major (consecutive blocked rows map to non-consecutive original rows) and full lines
+// when it is row-major.
+__global__ void permute_rows_kernel(const float* __restrict__ src, int64_t src_sr, int64_t src_sj,
+                                    float* __restrict__ dst, int64_t dst_sr, int64_t dst_sj,
+                                    const int64_t* __restrict__ row_map, int64_t rows, int64_t n) {
+  const int64_t total = rows * n;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t r, j;
+    if (src_sr == 1) { r = i % rows; j = i / rows; } else { j = i % n; r = i / n; }
+    dst[row_map[r] * dst_sr + j * dst_sj] = src[r * src_sr + j * src_sj];
+  }
+}
+
+cudaError_t permute_rows(const float* src, int64_t src_sr, int64_t src_sj, float* dst, int64_t dst_sr,
+                         int64_t dst_sj, const int64_t* row_map_dev, int64_t rows, int64_t n,
+                         cudaStream_t stream) {
+  if (rows == 0 || n == 0) return cudaSuccess;
+  const int64_t total = rows * n;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  permute_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(src, src_sr, src_sj, dst, dst_sr, dst_sj,
+                                                                     row_map_dev, rows, n);
+  return cudaGetLastError();
+}
+
 }  // namespace sparta

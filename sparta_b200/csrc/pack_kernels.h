@@ -12,4 +12,11 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
                       int64_t ldk, int64_t k_total, int64_t n, int precision,
                       cudaStream_t stream, bool keep_fp32 = false);
 
+// dst[row_map[r]] = src row r for r < rows: C back in the ORIGINAL row order (row_map = the
+// reference's get_permutation, utilities.cpp:8-20).  Both matrices have n columns and arbitrary
+// element strides (row stride sr, column stride sj).
+cudaError_t permute_rows(const float* src, int64_t src_sr, int64_t src_sj, float* dst, int64_t dst_sr,
+                         int64_t dst_sj, const int64_t* row_map_dev, int64_t rows, int64_t n,
+                         cudaStream_t stream);
+
 }  // namespace sparta

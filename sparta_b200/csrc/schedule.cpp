@@ -155,8 +155,10 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         merged.emplace_back(br.col[q], static_cast<int>(s - s0));
     }
     std::sort(merged.begin(), merged.end());
-    // pipeline fill + epilogue drain
-    const double fixed = 400.0 + 14.0 * cols;
+    // Per work item: draining the accumulator (measured 20.4 k cycles for 512 columns while the
+    // other SMs keep the L2 busy; the stores, not the TMEM reads, are the limit -- see
+    // scripts/microbench/epilogue_rate.cu) plus the tensor pipe running dry and refilling.
+    const double fixed = 10000.0 + 40.0 * cols;
     double cost = fixed;
     size_t i = 0;
     while (i < merged.size()) {
@@ -241,10 +243,12 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         st.a_bytes += bytes;
         st.max_chunk_bytes = std::max(st.max_chunk_bytes, share);
         st.chunks.push_back(ch);
-        // modelled cycles per CTA: tensor pipe N/2 per K step; L2 -> smem at ~40 B/cycle/SM
+        // modelled cycles per CTA: tensor pipe N/2 per K step; L2 -> smem: fitted to the kernel
+        // times of 29 shards of the bench matrix (scripts/fit_cost_model.py): 490 cycles per chunk
+        // + 1.27 per staged row of A in pair mode (64 bytes per row and CTA => ~50 B/cycle/SM)
         const double tensor = ch.ksteps * (rows_present * 0.5);
-        const double memory = (kPanelBytes + share) / 40.0;
-        st.chunk_cost.push_back(static_cast<float>(std::max(tensor, memory) + 30.0));
+        const double memory = 160.0 + (kPanelBytes + share) / 50.0;
+        st.chunk_cost.push_back(static_cast<float>(std::max(tensor, memory)));
         cost += st.chunk_cost.back();
       }
       i = i1;
@@ -290,16 +294,16 @@ struct TeamPlan {
   int cut_units = 0;
 };
 
-int pick_team(int workers, int64_t tiles, int64_t fit) {
+// Team width = column tiles per group: the largest divisor of the tile count whose B slab fits.
+// The worker count is rounded DOWN to a multiple of the team width (74 CTA pairs run as 18 teams
+// of 4): measured on the bench matrix, teams of 4 on 144 CTAs beat teams of 2 on 148 by 4-5 % on
+// quarter and eighth shards and tie on the whole matrix -- wider teams halve the number of groups,
+// i.e. the work items per worker and the passes of A through HBM.
+int pick_team(int* workers, int64_t tiles, int64_t fit) {
   int team = 1;
-  for (int t = 1; t <= workers && t <= fit; ++t)
-    if (workers % t == 0) team = t;
-  if (fit >= tiles && tiles <= workers) {
-    // the whole of B fits: one group; teams as wide as the tile count allows
-    team = 1;
-    for (int t = 1; t <= tiles; ++t)
-      if (workers % t == 0 && tiles % t == 0) team = t;
-  }
+  for (int t = 1; t <= *workers && t <= fit && t <= tiles; ++t)
+    if (tiles % t == 0) team = t;
+  *workers = *workers / team * team;
   return team;
 }
 
@@ -434,19 +438,28 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
   as.cta_ptr.assign(1, 0);
   if (n_srows == 0) return "";
 
-  // column tiles per group: the largest divisor of the worker count whose slab fits
+  // column tiles per group: as many as keep the group's slab of B (k_total x group width) within
+  // the L2 budget.  The budget (default 160 MB) is deliberately above the 126 MB of L2: the workers
+  // sweep k upwards roughly in step, so the panels in use at any time are a moving band of the
+  // slab, not all of it (measured on the bench matrix: a 268 MB slab still ran at full speed).
   const double tile_bytes = static_cast<double>(k_total) * tile * prec_esize(opt.precision);
   int64_t fit = std::max<int64_t>(1, static_cast<int64_t>(opt.l2_slab_bytes / std::max(tile_bytes, 1.0)));
   fit = std::min(fit, tiles);
 
-  std::vector<int32_t> by_cost(n_srows);
-  for (int64_t s = 0; s < n_srows; ++s) by_cost[s] = static_cast<int32_t>(s);
+  // Super-rows without a single nonzero block get no work item: their rows of C are zero after
+  // the memset that follows every (re)allocation of C (set_B), nothing else ever writes them, and
+  // with accumulate = 1 adding zero is a no-op.  (On the R-MAT bench matrix a fifth of the rows
+  // are empty; draining an all-zero accumulator for each of them cost more than their share.)
+  std::vector<int32_t> by_cost;
+  for (int64_t s = 0; s < n_srows; ++s)
+    if (st.srows[s].chunk_count > 0) by_cost.push_back(static_cast<int32_t>(s));
+  if (by_cost.empty()) return "";
   std::stable_sort(by_cost.begin(), by_cost.end(),
                    [&](int32_t a, int32_t b) { return st.srow_cost[a] > st.srow_cost[b]; });
 
   TeamPlan whole, split;
-  whole.workers = static_cast<int>(std::min<int64_t>(all_workers, n_srows * tiles));
-  whole.team = pick_team(whole.workers, tiles, fit);
+  whole.workers = static_cast<int>(std::min<int64_t>(all_workers, static_cast<int64_t>(by_cost.size()) * tiles));
+  whole.team = pick_team(&whole.workers, tiles, fit);
   plan_whole(st, by_cost, (tiles + whole.team - 1) / whole.team, &whole);
   const TeamPlan* tp = &whole;
   if (opt.split != 1) {
@@ -454,7 +467,7 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
     for (const SuperRow& sr : st.srows) n_chunks += sr.chunk_count;
     // no more workers than pieces of >= 16 chunks
     split.workers = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(all_workers, n_chunks * tiles / 16)));
-    split.team = pick_team(split.workers, tiles, fit);
+    split.team = pick_team(&split.workers, tiles, fit);
     plan_split(st, by_cost, (tiles + split.team - 1) / split.team, &split);
     const bool pays = split.max_cost < 0.95 * whole.max_cost;   // the worker that finishes last sets the time
     if (opt.split == 2 || pays) tp = &split;

@@ -35,7 +35,7 @@ struct ScheduleOptions {
   int num_ctas = 148;      // persistent grid size upper bound
   int pair = 1;            // 1: two CTAs (one TPC) share a super-row through tcgen05 cta_group::2
   int sort_rows = 1;       // 1: group block-rows of similar nonzero-block count into super-rows
-  int64_t l2_slab_bytes = 64ll << 20;  // B columns kept L2-resident at a time (see build_assignment)
+  int64_t l2_slab_bytes = 160ll << 20;  // B columns kept L2-resident at a time (see build_assignment)
   int max_chain = 0;       // longest accumulation chain in tcgen05.mma instructions (0: default, -1: unlimited)
   int split = 0;           // chunk lists split between workers: 0 when the model says it pays, 1 never, 2 always
 };

@@ -544,6 +544,43 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
     uint32_t acc_use[2] = {0, 0};
     int local = 0;
     const bool c_aligned = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+    bool zero_seen = p.n_zero_jobs == 0;
+    if (p.n_zero_jobs > 0) {
+      // this CTA's share of the tiles that split pieces add into (see SpmmParams::zero_jobs);
+      // it runs while the producer and MMA warps work on the first item
+      const int et = static_cast<int>(threadIdx.x) - 64;   // 0..127 over the four epilogue warps
+      constexpr int kHalves = kPair ? 2 : 1;
+      for (int u = blockIdx.x; u < p.n_zero_jobs * kHalves; u += gridDim.x) {
+        const ZeroJob job = p.zero_jobs[u / kHalves];
+        const int j0 = job.j0 + (u % kHalves) * kTileJ;
+        const int jn = min(kTileJ, p.n - j0);
+        if (jn <= 0) continue;
+        const SuperRow zr = p.srows[job.srow];
+        for (int sidx = 0; sidx < zr.seg_count; ++sidx) {
+          const Segment sg = p.segs[zr.seg_begin + sidx];
+          if (c_aligned && p.c_sr == 1 && (p.c_sj & 3) == 0 && (sg.c_row0 & 3) == 0 && (sg.h & 3) == 0) {
+            const int q4 = sg.h >> 2;   // 16-byte pieces per column; lanes run along the rows
+            for (int i = et; i < jn * q4; i += 128) {
+              const int jj = i / q4, r4 = i - jj * q4;
+              reinterpret_cast<float4*>(p.C + static_cast<int64_t>(j0 + jj) * p.c_sj + sg.c_row0)[r4] =
+                  make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
+            for (int i = et; i < jn * sg.h; i += 128) {
+              int r, jj;
+              if (p.c_sr == 1) { jj = i / sg.h; r = i - jj * sg.h; } else { r = i / jn; jj = i - r * jn; }
+              p.C[static_cast<int64_t>(sg.c_row0 + r) * p.c_sr + static_cast<int64_t>(j0 + jj) * p.c_sj] = 0.0f;
+            }
+          }
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        __threadfence();
+        atomicAdd(p.sync_counter, 1ULL);
+      }
+    }
     float* stg = reinterpret_cast<float*>(ctrl + kSmemStageOff) + (warp - 2) * 512;   // 32 x 16 floats
     for (int it = it_begin; it < it_end; ++it, ++local) {
       const Item item = load_item(p, it);
@@ -555,6 +592,26 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       const bool to_master = (item.count & kItemNotLast) != 0;
       const bool add_c = p.accumulate != 0;
       const bool red_c = (item.count & kItemAtomic) != 0;   // a split piece: C += partial sums
+      if (red_c && !zero_seen) {
+        // every CTA must have zeroed its share of the split tiles before the first reduction
+        if (lane == 0) {
+          const uint64_t t0 = global_timer_ns();
+          unsigned long long seen;
+          uint32_t spins = 0;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(p.sync_counter) : "memory");
+            if (seen >= p.sync_target) break;
+            if (((++spins) & 0xFF) == 0 && global_timer_ns() - t0 > 5000000000ull) {
+              printf("sparta spmm: split tiles were not zeroed in time (cta %d, %llu of %llu)\n", blockIdx.x, seen,
+                     p.sync_target);
+              __trap();
+            }
+            __nanosleep(200);
+          }
+        }
+        __syncwarp();
+        zero_seen = true;
+      }
       mbar_wait(bar_acc_full + 8 * as, acc_use[as] & 1, 5);
       const unsigned long long te0 = (tr && warp == 2 && lane == 0) ? sm_clock() : 0ull;
       ++acc_use[as];
@@ -563,76 +620,118 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       const int j = item.j0 + static_cast<int>(rank) * kTileJ + q * 32 + lane;
       const bool jv = j < p.n;
       float* cj = p.C + static_cast<int64_t>(j) * p.c_sj;
-      for (int sidx = 0; sidx < sr.seg_count; ++sidx) {
-        const Segment sg = p.segs[sr.seg_begin + sidx];
+      // The segment records of the super-row, one per lane, broadcast by shuffle below: a global
+      // load per segment inside the loop put an L2 round trip on the critical path of the drain.
+      int4 seg_mine = make_int4(0, 0, 0, 0);
+      if (lane < sr.seg_count) seg_mine = __ldg(reinterpret_cast<const int4*>(p.segs + sr.seg_begin) + lane);
+      auto segment = [&](int sidx) {
+        Segment sg;
+        sg.c_row0 = __shfl_sync(0xFFFFFFFFu, seg_mine.x, sidx);
+        sg.h = __shfl_sync(0xFFFFFFFFu, seg_mine.y, sidx);
+        sg.h_pad = __shfl_sync(0xFFFFFFFFu, seg_mine.z, sidx);
+        sg.tmem_col = __shfl_sync(0xFFFFFFFFu, seg_mine.w, sidx);
+        return sg;
+      };
+      // 16 accumulator columns (rows c0.. of segment sg, column j of C per lane) -> C
+      auto store16 = [&](const uint32_t (&v)[16], const Segment& sg, int c0) {
         const bool vec_ok = c_aligned && p.c_sr == 1 && (p.c_sj & 3) == 0 && (sg.c_row0 & 3) == 0;
-        for (int c0 = 0; c0 < sg.h_pad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + sg.tmem_col + c0, v);
-          if (fold_in) {
-            uint32_t m[16];
-            tmem_ld16(t_acc + p.master_col + sg.tmem_col + c0, m);
-            tmem_wait_ld();
+        if (vec_ok && c0 + 16 <= sg.h) {
+          // Column-major C: a thread owns one column j, so its 16 values are 64 contiguous bytes
+          // but the warp's 32 columns are 32 different lines.  Transposed through a 2 KB per-warp
+          // staging tile (XOR-swizzled, conflict-free both ways) 4 lanes cover a column's 64
+          // bytes and one store instruction touches 8 lines instead of 32.
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
-              v[r] = __float_as_uint(__fadd_rn(__uint_as_float(v[r]), __uint_as_float(m[r])));
-          } else {
-            tmem_wait_ld();
-          }
-          tmem_st16_zero(t_acc + sg.tmem_col + c0);
-          if (to_master) {
-            tmem_st16(t_acc + p.master_col + sg.tmem_col + c0, v);
-            continue;
-          }
-          if (vec_ok && c0 + 16 <= sg.h) {
-            // Column-major C: a thread owns one column j, so its 16 values are 64 contiguous
-            // bytes but the warp's 32 columns are 32 different lines -- stored straight from the
-            // registers every st.v4 costs 32 LSU wavefronts (the first traces: 23 k cycles to
-            // drain 512 accumulator columns).  Transposed through a 2 KB per-warp staging tile
-            // (XOR-swizzled, conflict-free both ways) 4 lanes cover a column's 64 bytes and one
-            // instruction touches 8 lines instead of 32.
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (g ^ ((lane >> 1) & 3))) =
+                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                            __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          __syncwarp();
+          const int gl = lane & 3;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (g ^ ((lane >> 1) & 3))) =
-                  make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                              __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-            __syncwarp();
-            const int gl = lane & 3;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int jj = 8 * i + (lane >> 2);
-              float4 o = *reinterpret_cast<const float4*>(stg + jj * 16 + 4 * (gl ^ ((jj >> 1) & 3)));
-              const int jcol = j - lane + jj;
-              if (jcol < p.n) {
-                float4* d4 = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(jcol) * p.c_sj +
-                                                       (sg.c_row0 + c0 + 4 * gl));
-                if (red_c) {
-                  red_add_v4(d4, o);
-                } else {
-                  if (add_c) {
-                    const float4 old = *d4;
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                  }
-                  *d4 = o;
+          for (int i = 0; i < 4; ++i) {
+            const int jj = 8 * i + (lane >> 2);
+            float4 o = *reinterpret_cast<const float4*>(stg + jj * 16 + 4 * (gl ^ ((jj >> 1) & 3)));
+            const int jcol = j - lane + jj;
+            if (jcol < p.n) {
+              float4* d4 = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(jcol) * p.c_sj +
+                                                     (sg.c_row0 + c0 + 4 * gl));
+              if (red_c) {
+                red_add_v4(d4, o);
+              } else {
+                if (add_c) {
+                  const float4 old = *d4;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                 }
+                *d4 = o;
               }
             }
-            __syncwarp();
-          } else if (jv) {
-            float* dst = cj + static_cast<int64_t>(sg.c_row0 + c0) * p.c_sr;
+          }
+          __syncwarp();
+        } else if (jv) {
+          float* dst = cj + static_cast<int64_t>(sg.c_row0 + c0) * p.c_sr;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              if (c0 + r < sg.h) {
-                float o = __uint_as_float(v[r]);
-                float* d = dst + static_cast<int64_t>(r) * p.c_sr;
-                if (red_c) {
-                  red_add(d, o);
-                } else {
-                  if (add_c) o += *d;
-                  *d = o;
-                }
+          for (int r = 0; r < 16; ++r) {
+            if (c0 + r < sg.h) {
+              float o = __uint_as_float(v[r]);
+              float* d = dst + static_cast<int64_t>(r) * p.c_sr;
+              if (red_c) {
+                red_add(d, o);
+              } else {
+                if (add_c) o += *d;
+                *d = o;
               }
             }
+          }
+        }
+      };
+      if (fold_in || to_master) {
+        // bounded accumulation chains (the tf32 default): fold through the master accumulators
+        for (int sidx = 0; sidx < sr.seg_count; ++sidx) {
+          const Segment sg = segment(sidx);
+          for (int c0 = 0; c0 < sg.h_pad; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_acc + sg.tmem_col + c0, v);
+            if (fold_in) {
+              uint32_t m[16];
+              tmem_ld16(t_acc + p.master_col + sg.tmem_col + c0, m);
+              tmem_wait_ld();
+#pragma unroll
+              for (int r = 0; r < 16; ++r)
+                v[r] = __float_as_uint(__fadd_rn(__uint_as_float(v[r]), __uint_as_float(m[r])));
+            } else {
+              tmem_wait_ld();
+            }
+            tmem_st16_zero(t_acc + sg.tmem_col + c0);
+            if (to_master) tmem_st16(t_acc + p.master_col + sg.tmem_col + c0, v);
+            else store16(v, sg, c0);
+          }
+        }
+      } else {
+        // Plain drain, software-pipelined: the accumulator columns of a super-row are contiguous
+        // (tmem_col = running sum of h_pad), step s covers columns [16 s, 16 s + 16).  The load of
+        // step s+1 is in flight while step s is stored; tcgen05.wait::ld sits right before the
+        // first use of a buffer and nothing touches the buffer between its load and that wait.
+        const int nsteps = sr.n_cols >> 4;
+        int sidx = 0, c0 = 0;
+        Segment sg = segment(0);
+        auto advance = [&]() {
+          c0 += 16;
+          if (c0 >= sg.h_pad && sidx + 1 < sr.seg_count) { ++sidx; sg = segment(sidx); c0 = 0; }
+        };
+        uint32_t va[16], vb[16];
+        if (nsteps > 0) tmem_ld16(t_acc, va);
+        for (int st = 0; st < nsteps; st += 2) {
+          tmem_wait_ld();
+          if (st + 1 < nsteps) tmem_ld16(t_acc + 16 * (st + 1), vb);
+          tmem_st16_zero(t_acc + 16 * st);
+          store16(va, sg, c0);
+          advance();
+          if (st + 1 < nsteps) {
+            tmem_wait_ld();
+            if (st + 2 < nsteps) tmem_ld16(t_acc + 16 * (st + 2), va);
+            tmem_st16_zero(t_acc + 16 * (st + 1));
+            store16(vb, sg, c0);
+            advance();
           }
         }
       }
@@ -662,34 +761,6 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
                    : "memory");
     }
   }
-}
-
-// ------------------------------------------------------------------ zeroing of split tiles
-// One block per job: the rows of the job's super-row x `tile` columns of C.  Rows of a segment
-// are contiguous when C is column-major (c_sr == 1), columns when it is row-major (c_sj == 1);
-// threads run along whichever is contiguous.
-__global__ void zero_c_tiles_kernel(const ZeroJob* __restrict__ jobs, const SuperRow* __restrict__ srows,
-                                    const Segment* __restrict__ segs, float* __restrict__ C,
-                                    int64_t c_sr, int64_t c_sj, int n, int tile) {
-  const ZeroJob job = jobs[blockIdx.x];
-  const SuperRow sr = srows[job.srow];
-  const int jn = min(tile, n - job.j0);
-  for (int sidx = 0; sidx < sr.seg_count; ++sidx) {
-    const Segment sg = segs[sr.seg_begin + sidx];
-    const int total = sg.h * jn;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      int r, j;
-      if (c_sr == 1) { r = i % sg.h; j = i / sg.h; } else { j = i % jn; r = i / jn; }
-      C[static_cast<int64_t>(sg.c_row0 + r) * c_sr + static_cast<int64_t>(job.j0 + j) * c_sj] = 0.0f;
-    }
-  }
-}
-
-cudaError_t zero_c_tiles_launch(const SpmmParams& p, const ZeroJob* jobs, int n_jobs, cudaStream_t stream) {
-  if (n_jobs <= 0) return cudaSuccess;
-  zero_c_tiles_kernel<<<n_jobs, 512, 0, stream>>>(jobs, p.srows, p.segs, p.C, p.c_sr, p.c_sj, p.n,
-                                                   p.pair ? 2 * kTileJ : kTileJ);
-  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ launch

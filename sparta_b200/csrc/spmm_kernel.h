@@ -27,6 +27,15 @@ struct SpmmParams {
   int32_t         acc_stage_cols; // 512 / acc_stages
   int32_t         master_col;   // > 0: TMEM column offset of the master accumulators (bounded chains)
   int32_t         pair;         // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2); cta_ptr is per pair
+  // Split pieces (kItemAtomic) add into C tiles that must start from zero.  Every CTA zeroes its
+  // share of those tiles in its epilogue warps while its first item is still in the tensor pipe,
+  // then bumps *sync_counter; a warp about to issue its first reduction waits until the counter
+  // has reached sync_target (= all CTAs of all launches so far).  All CTAs of the grid are
+  // co-resident (one per SM), so the wait cannot deadlock.
+  const ZeroJob*  zero_jobs;
+  int32_t         n_zero_jobs;
+  unsigned long long* sync_counter;
+  unsigned long long  sync_target;
   // optional timeline of one worker (sparta_run_traced): 4 zones x 2 ranks x trace_cap records of
   // {t0, t1} SM clocks; zone 0 producer per chunk, 1 MMA per chunk, 2 epilogue per item,
   // 3 MMA accumulator wait per item
@@ -53,9 +62,5 @@ static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes) {
 cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
                         int64_t ldk, int precision, int grid, cudaStream_t stream,
                         const char** err);
-
-// Zeroes the C tiles that split pieces (kItemAtomic) accumulate into: the rows of each job's
-// super-row, columns [j0, j0 + tile).  Uses p.srows / p.segs / p.C / strides / n / pair.
-cudaError_t zero_c_tiles_launch(const SpmmParams& p, const ZeroJob* jobs, int n_jobs, cudaStream_t stream);
 
 }  // namespace sparta

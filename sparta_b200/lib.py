@@ -72,6 +72,7 @@ SIGNATURES = {
     "sparta_run_traced": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
     "sparta_synchronize": (C.c_int, [_vp]),
     "sparta_get_C": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
+    "sparta_get_C_permuted": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int]),
     "sparta_C_device_ptr": (_vp, [_vp]),
     "sparta_C_device_ld": (C.c_int64, [_vp]),
     "sparta_stream": (_vp, [_vp]),
@@ -90,6 +91,8 @@ SIGNATURES = {
                                   C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "sparta_release_workspace": (C.c_int, []),
     "sparta_partition_block_rows": (C.c_int, [C.c_int64, _vp, _vp, C.c_int32, _vp]),
+    "sparta_partition_block_rows_modelled": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp,
+                                                       C.c_int64, C.POINTER(Options), C.c_int32, _vp]),
     "sparta_host_blocking": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
                                        C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp]),
@@ -170,6 +173,16 @@ def partition_block_rows(row_part, nzcount, parts):
     cuts = np.zeros(parts + 1, dtype=np.int64)
     _check(load().sparta_partition_block_rows(len(nzcount), _ptr(row_part), _ptr(nzcount), parts,
                                               _ptr(cuts)))
+    return cuts
+
+
+def partition_block_rows_modelled(rows, cols, block_col_size, row_part, nzcount, jab, n, parts, **opts):
+    """Contiguous block-row ranges balanced on the scheduler's modelled shard times."""
+    row_part, nzcount, jab = _i64(row_part), _i64(nzcount), _i64(jab)
+    cuts = np.zeros(parts + 1, dtype=np.int64)
+    o = make_options(**opts)
+    _check(load().sparta_partition_block_rows_modelled(rows, cols, len(nzcount), block_col_size, _ptr(row_part),
+                                                       _ptr(nzcount), _ptr(jab), n, C.byref(o), parts, _ptr(cuts)))
     return cuts
 
 
@@ -260,6 +273,14 @@ class Handle:
     def get_C(self, out, ld):
         assert out.dtype == np.float32 and out.flags.c_contiguous
         _check(load().sparta_get_C(self._h, _ptr(out), ld, 0))
+        return out
+
+    def get_C_permuted(self, out, ld, row_map, out_rows):
+        """C with row r of the handle written to row row_map[r] of `out` (original row order);
+        `out` has out_rows rows in the handle's C layout."""
+        row_map = _i64(row_map)
+        assert out.dtype == np.float32 and out.flags.c_contiguous
+        _check(load().sparta_get_C_permuted(self._h, _ptr(out), ld, _ptr(row_map), out_rows, 0))
         return out
 
     def get_C_device(self, dptr, ld):

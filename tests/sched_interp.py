@@ -73,6 +73,11 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
         sr = srows[key[0]]
         for sg in segs[sr["seg_begin"]:sr["seg_begin"] + sr["seg_count"]]:
             Cm[key[1]:key[1] + tile, sg["c_row0"]:sg["c_row0"] + sg["h"]] = 0.0
+    # super-rows without any block get no item: their rows keep C's initial zero fill
+    for sr in srows:
+        if int(sr["chunk_count"]) == 0:
+            for sg in segs[sr["seg_begin"]:sr["seg_begin"] + sr["seg_count"]]:
+                Cm[:, sg["c_row0"]:sg["c_row0"] + sg["h"]] = 0.0
     covered = {}       # (srow, j0) -> [(first chunk, chunks)] over all pieces
     n_atomic = 0
     for worker in range(len(plan["cta_ptr"]) - 1):
@@ -90,7 +95,7 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
             atomic = bool(int(item["count"]) & ATOMIC)
             key = (int(item["srow"]), int(item["j0"]))
             covered.setdefault(key, []).append((off, cnt))
-            assert key[1] % tile == 0 and (cnt > 0 or int(sr["chunk_count"]) == 0)
+            assert key[1] % tile == 0 and cnt > 0
             # passes of one piece run back to back on one worker, in chunk order
             if fold_in:
                 assert open_pass == (key[0], key[1], off)
@@ -159,7 +164,7 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
     assert visited.all()
     # every (super-row, column tile): its pieces tile the chunk list exactly once
     n_tiles = (n + tile - 1) // tile
-    assert len(covered) == len(srows) * n_tiles
+    assert len(covered) == int((srows["chunk_count"] > 0).sum()) * n_tiles
     for (s_id, _), ranges in covered.items():
         pos = 0
         for off, cnt in sorted(ranges):
