@@ -46,6 +46,10 @@ WORKLOADS = {
     "er14_fixed": dict(kind="er", scale=14, density=2.57e-5, w=64, rb=64, tau=0.0, n=1024, algo=2,
                        desc="ER 16384x16384 p=2.57e-5 seed 1, -a 2 -F 1 -b 64 -B 64 (10% block density), "
                             "B 16384x1024"),
+    "rmat16_a4": dict(kind="rmat", scale=16, density=1e-3, w=64, rb=64, tau=0.6, n=4096, algo=4,
+                      desc="BASELINE config #4 at a quarter of its side: R-MAT 65536x65536 (same generator), "
+                           "-P 1 -a 4 -b 64 -t 0.6 (variable-height VBR: 33 605 block-rows, 90% of height 1, tallest 13 043), "
+                           "B 65536x4096"),
     "rmat12_a5": dict(kind="rmat", scale=12, density=4e-3, w=64, rb=64, tau=0.6, n=512, algo=5,
                       desc="small R-MAT 4096x4096 for quick checks"),
 }

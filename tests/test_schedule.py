@@ -200,3 +200,32 @@ def test_inverted_product_plan_matches_oracle(oracle, lib, case, precision, esiz
     assert np.array_equal(Cm, Cref.T)
     from tests.util import vbr_to_dense
     assert np.array_equal(Cref, (Bt.T.astype(np.float64) @ vbr_to_dense(v)).T.astype(np.float32))
+
+
+def test_modelled_partition_is_contiguous_and_no_worse_than_area(lib):
+    """sparta_partition_block_rows_modelled: cuts are monotone, cover every block-row, and the
+    slowest shard's modelled time is not above the area partition's."""
+    rng = np.random.default_rng(71)
+    heights = [64] * 120
+    # dense head, sparse tail: equal areas are not equal times
+    dens = np.concatenate([np.full(30, 0.9), np.full(90, 0.08)])
+    rows = 0
+    row_part, nzcount, jab = [0], [], []
+    for b, h in enumerate(heights):
+        cols = np.flatnonzero(rng.random(128) < dens[b])
+        nzcount.append(len(cols)); jab.extend(cols.tolist()); rows += h; row_part.append(rows)
+    row_part, nzcount, jab = np.array(row_part), np.array(nzcount), np.array(jab)
+    n = 1024
+    for parts in (2, 4):
+        area = sparta_b200.partition_block_rows(row_part, nzcount, parts)
+        model = sparta_b200.partition_block_rows_modelled(rows, 128 * 64, 64, row_part, nzcount, jab, n, parts)
+        assert model[0] == 0 and model[-1] == len(nzcount) and np.all(np.diff(model) >= 0)
+
+        def worst(cuts):
+            t = []
+            for i in range(parts):
+                p = sparta_b200.vbr_plan(rows, 128 * 64, 64, row_part, nzcount, jab, n,
+                                         block_row_begin=int(cuts[i]), block_row_end=int(cuts[i + 1]))
+                t.append(p["stats"]["sched_max_cycles"])
+            return max(t)
+        assert worst(model) <= worst(area) * 1.001

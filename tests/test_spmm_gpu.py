@@ -466,3 +466,29 @@ def test_unpermuted_read_back_equals_csr_multiply(oracle, lib, layout):
             assert np.array_equal(out, Cref.T)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_variable_height_blocking_end_to_end(oracle, lib, precision):
+    """BASELINE config #4's shape at small scale: edge list -> the library's own `-a 4` clustering
+    (bit-exact with the reference, tests/test_blocking.py) -> variable-height VBR (most block-rows
+    one row tall, a few hundreds of rows tall) -> multiply, against the oracle on the same VBR."""
+    from sparta_b200.lib import host_blocking, host_vbr_fill
+    N = 1 << 12
+    r, c = synth.rmat_edges(12, int(4e-3 * N * N), seed=3)
+    r, c = synth.pin_shape(r, c, N, N)
+    rowptr, colind, _ = synth.csr_from_edges(r, c, N)
+    g = host_blocking(N, N, rowptr, colind, algo=4, tau=0.6, block_col_size=64, row_block_size=64,
+                      sim_measure=1, use_pattern=True, use_group=False)
+    v = host_vbr_fill(N, N, rowptr, colind, None, g, 64, 64, force_fixed_size=False, pattern_only=True)
+    heights = np.diff(v["row_part"])
+    assert (heights == 1).mean() > 0.5 and heights.max() > 64          # the shape the test is about
+    n = 320
+    rng = np.random.default_rng(61)
+    Bm = rng.integers(-3, 4, size=(n, N)).astype(np.float32)
+    Cg = gpu_multiply(v, Bm, n, precision)
+    assert np.array_equal(Cg, oracle.vbr_multiply(v, Bm, n))
+    # real operands, tf32 tolerance of the north star (<= 1e-5 against the rounded operands)
+    Br = rng.random((n, N), dtype=np.float32)
+    Cg = gpu_multiply(v, Br, n, precision)
+    assert rel_err(Cg, oracle.vbr_multiply(v, round_to(Br, precision), n)) <= TOL_ROUNDED
