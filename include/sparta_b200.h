@@ -67,7 +67,10 @@ typedef struct sparta_options {
                             lists into equal-cost pieces, one per worker, partial sums added to C with
                             fp32 reductions.  0: when the cost model says it pays (default), 1: never,
                             2: always */
-  int32_t reserved[3];
+  int32_t fuse_rows;     /* runs of consecutive block-rows whose heights add up to <= 16 share one 16-row MMA
+                            segment with the union of their column-block lists (variable-height blockings
+                            produce thousands of block-rows one or two rows tall).  0: on (default), 1: off */
+  int32_t reserved[2];
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */

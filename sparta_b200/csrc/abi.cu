@@ -333,6 +333,67 @@ static int open_handle(sparta_handle** out, const sparta_options& o, int* sms_ou
   return SPARTA_OK;
 }
 
+// ---- sparse upload of a mostly-zero fp32 source -------------------------------------------------
+struct SparseSource {
+  std::vector<std::vector<int64_t>> idx;   // per scanning thread: element offsets of the nonzeros
+  std::vector<std::vector<float>> val;
+  int64_t total = 0;
+};
+
+// fraction of nonzero elements in ~256 K sampled elements (4096 windows of 64)
+static double sampled_density(const float* src, int64_t n) {
+  const int64_t windows = 4096, len = 64;
+  if (n < windows * len) return 1.0;
+  int64_t nz = 0;
+  uint64_t x = 0x9E3779B97F4A7C15ull;
+  for (int64_t w = 0; w < windows; ++w) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    const int64_t at = static_cast<int64_t>(x % static_cast<uint64_t>(n - len));
+    for (int64_t i = 0; i < len; ++i) nz += src[at + i] != 0.0f;
+  }
+  return static_cast<double>(nz) / static_cast<double>(windows * len);
+}
+
+// All host threads scan disjoint ranges; gives up (returns false) as soon as the source turns
+// out denser than the sample suggested (12 bytes per nonzero against 4 per element).
+static bool scan_nonzeros(const float* src, int64_t n, SparseSource* out) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const int T = static_cast<int>(std::max(1u, std::min(hw ? hw : 8u, 32u)));
+  out->idx.assign(T, {});
+  out->val.assign(T, {});
+  std::vector<char> gave_up(T, 0);
+  const int64_t limit = n / 5 / T + 1024;   // per thread: at most 20 % nonzeros
+  auto work = [&](int t) {
+    const int64_t lo = n * t / T, hi = n * (t + 1) / T;
+    std::vector<int64_t>& ix = out->idx[t];
+    std::vector<float>& vl = out->val[t];
+    ix.reserve(static_cast<size_t>((hi - lo) / 64 + 1024));
+    vl.reserve(static_cast<size_t>((hi - lo) / 64 + 1024));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src);
+    int64_t i = lo;
+    for (; i + 16 <= hi; i += 16) {
+      uint32_t any = 0;
+      for (int e = 0; e < 16; ++e) any |= w[i + e];
+      if (!(any & 0x7FFFFFFFu)) continue;      // +0 / -0 only
+      for (int e = 0; e < 16; ++e)
+        if (w[i + e] & 0x7FFFFFFFu) { ix.push_back(i + e); vl.push_back(src[i + e]); }
+      if (static_cast<int64_t>(ix.size()) > limit) { gave_up[t] = 1; return; }
+    }
+    for (; i < hi; ++i)
+      if (w[i] & 0x7FFFFFFFu) { ix.push_back(i); vl.push_back(src[i]); }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  out->total = 0;
+  for (int t = 0; t < T; ++t) {
+    if (gave_up[t]) return false;
+    out->total += static_cast<int64_t>(out->idx[t].size());
+  }
+  return true;
+}
+
 // The host tile scheduler (tens of milliseconds at 10^5 blocks) runs on its own thread WHILE the
 // fp32 source crosses PCIe; nothing on the device waits for the CPU afterwards except the small
 // schedule arrays.  No stream synchronisation happens here: the caller's next set_B / run /
@@ -368,7 +429,11 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->block_rows = br.count();
 
   const char* serr = "";
-  std::thread sched([&] { serr = build_structure(br, h->sopt, &h->st); });
+  // runs of short consecutive block-rows share one 16-row MMA segment (schedule.h)
+  BlockRows fused;
+  const BlockRows* view = &br;
+  if (o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused)) view = &fused;
+  std::thread sched([&, view] { serr = build_structure(*view, h->sopt, &h->st); });
 
 #define H_TRY(call)                                                            \
   do {                                                                         \
@@ -386,11 +451,42 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   float* d_src = nullptr;
   PackJob* d_jobs = nullptr;
   H_TRY(cudaEventRecord(h->up0, h->stream));
+  bool sparse_upload = false;
   if (src_elems > 0) {
     // Stage the fp32 source on the device; it is repacked into MMA-ready images there.
     H_TRY(dev_alloc(&d_src, static_cast<size_t>(src_elems) * sizeof(float), h->stream));
-    H_TRY(cudaMemcpyAsync(d_src, src_host, static_cast<size_t>(src_elems) * sizeof(float),
-                          cudaMemcpyHostToDevice, h->stream));
+    // The blocks SPARTA's clustering produces are mostly zeros inside (config #3: 3.5 M nonzeros
+    // in 1.1 G stored elements), and PCIe is the slowest link of a one-shot call: when a sample
+    // says the source is sparse, the host threads pick out the nonzeros (a read of the array at
+    // memory speed), only those cross PCIe, and the dense image is rebuilt on the device.
+    SparseSource sp;
+    if (src_elems >= (int64_t{1} << 22) && !getenv("SPARTA_DENSE_UPLOAD") &&
+        sampled_density(src_host, src_elems) < 0.10 && scan_nonzeros(src_host, src_elems, &sp)) {
+      sparse_upload = true;
+      int64_t* d_idx = nullptr;
+      float* d_val = nullptr;
+      const int64_t nnz = sp.total;
+      H_TRY(cudaMemsetAsync(d_src, 0, static_cast<size_t>(src_elems) * sizeof(float), h->stream));
+      if (nnz > 0) {
+        H_TRY(dev_alloc(&d_idx, static_cast<size_t>(nnz) * sizeof(int64_t), h->stream));
+        H_TRY(dev_alloc(&d_val, static_cast<size_t>(nnz) * sizeof(float), h->stream));
+        int64_t at = 0;
+        for (size_t t = 0; t < sp.idx.size(); ++t) {
+          const size_t cnt = sp.idx[t].size();
+          if (!cnt) continue;
+          H_TRY(cudaMemcpyAsync(d_idx + at, sp.idx[t].data(), cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+          H_TRY(cudaMemcpyAsync(d_val + at, sp.val[t].data(), cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+          at += static_cast<int64_t>(cnt);
+        }
+        H_TRY(scatter_values(d_idx, d_val, nnz, d_src, h->stream));
+        // pageable sources are staged before cudaMemcpyAsync returns; the vectors may go away
+        dev_free(d_idx, h->stream);
+        dev_free(d_val, h->stream);
+      }
+    } else {
+      H_TRY(cudaMemcpyAsync(d_src, src_host, static_cast<size_t>(src_elems) * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+    }
   }
   sched.join();
   const auto tc1 = std::chrono::steady_clock::now();
@@ -407,6 +503,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
   H_TRY(upload_vec(h->st.tables, &h->d_tables, h->stream));
   H_TRY(dev_alloc(&h->d_a, h->st.a_bytes, h->stream));
+  if (h->st.sparse_images && h->st.a_bytes) H_TRY(cudaMemsetAsync(h->d_a, 0, h->st.a_bytes, h->stream));
   if (!h->st.jobs.empty()) {
     H_TRY(upload_vec(h->st.jobs, &d_jobs, h->stream));
     H_TRY(pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream));
@@ -418,7 +515,8 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   // The public create returns only when the caller's arrays are no longer being read.
   if (!defer_sync) H_TRY(cudaStreamSynchronize(h->stream));
   if (timing)
-    fprintf(stderr, "sparta create: host schedule + enqueue of the A upload %.1f ms, enqueue of the rest %.1f ms\n",
+    fprintf(stderr, "sparta create: host schedule + enqueue of the A upload (%s) %.1f ms, enqueue of the rest %.1f ms\n",
+            sparse_upload ? "nonzeros only" : "dense",
             std::chrono::duration<double, std::milli>(tc1 - tc0).count(),
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc1).count());
 #undef H_TRY
@@ -1119,7 +1217,9 @@ int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t blo
                                          &br, &src_lo, &src_hi);
       Structure st;
       Assignment as;
-      if (!*e) e = build_structure(br, so, &st);
+      BlockRows fused;
+      const bool use_fused = !*e && o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused);
+      if (!*e) e = build_structure(use_fused ? fused : br, so, &st);
       if (!*e) e = build_assignment(st, so, n, cols, &as);
       if (*e) return fail(SPARTA_ERR_INVALID, e);
       t[i] = as.max_cta_cost;
@@ -1269,7 +1369,11 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
   p->cols = cols; p->block_rows = br.count(); p->n = n;
   p->panel_stages = o.panel_stages;
   p->a_ring_bytes = ring_bytes_for(o.panel_stages);
-  e = build_structure(br, p->sopt, &p->st);
+  {
+    BlockRows fused;
+    const bool use_fused = o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused);
+    e = build_structure(use_fused ? fused : br, p->sopt, &p->st);
+  }
   if (!*e) e = build_assignment(p->st, p->sopt, n, cols, &p->as);
   if (*e) { delete p; return fail(SPARTA_ERR_INVALID, e); }
   *out = p;

@@ -30,17 +30,21 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, int precision) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// One CTA per image.  Thread t walks (row r fastest, 16-byte chunk c) so that
-// column-major sources are read coalesced along r.
+// One WARP per job (8 jobs per CTA): fused short block-rows produce millions of jobs of a row or
+// two, for which a CTA per job spent a second launching blocks.  Lane t walks (row r fastest,
+// 16-byte chunk c) so that column-major sources are read coalesced along r.
 __global__ void __launch_bounds__(256) pack_a_images_kernel(const float* __restrict__ src,
                                                             const PackJob* __restrict__ jobs,
+                                                            int64_t n_jobs,
                                                             uint8_t* __restrict__ dst,
                                                             int precision) {
-  const PackJob job = jobs[blockIdx.x];
+  const int64_t jid = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (jid >= n_jobs) return;
+  const PackJob job = jobs[jid];
   const int epc = (precision == PREC_TF32) ? 4 : 8;  // elements per 16-byte chunk
   uint8_t* out = dst + static_cast<size_t>(job.dst_off16) * 16;
   const int total = job.h_pad * 8;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+  for (int idx = threadIdx.x & 31; idx < total; idx += 32) {
     const int r = idx % job.h_pad;
     const int c = idx / job.h_pad;
     float v[8];
@@ -60,7 +64,8 @@ __global__ void __launch_bounds__(256) pack_a_images_kernel(const float* __restr
                      pack2(v[4], v[5], precision), pack2(v[6], v[7], precision));
     }
     // Swizzle<3,4,3>: 16-byte chunk index XOR (row mod 8) inside each 1024-byte atom
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * 128 + ((c ^ (r & 7)) << 4)) = o;
+    const int ro = job.r_base + r;   // row inside the image
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(ro) * 128 + ((c ^ (ro & 7)) << 4)) = o;
   }
 }
 
@@ -118,8 +123,8 @@ cudaError_t pack_a_images(const float* src_dev, const PackJob* jobs_dev, int64_t
   const int64_t kMaxGrid = 1 << 30;
   for (int64_t done = 0; done < n_jobs; done += kMaxGrid) {
     const int64_t g = (n_jobs - done < kMaxGrid) ? (n_jobs - done) : kMaxGrid;
-    pack_a_images_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(src_dev, jobs_dev + done,
-                                                                      dst_dev, precision);
+    pack_a_images_kernel<<<static_cast<unsigned>((g + 7) / 8), 256, 0, stream>>>(src_dev, jobs_dev + done, g,
+                                                                                dst_dev, precision);
   }
   return cudaGetLastError();
 }
@@ -150,6 +155,22 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
           precision);
     }
   }
+  return cudaGetLastError();
+}
+
+__global__ void scatter_values_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val, int64_t nnz,
+                                      float* __restrict__ dst) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += stride)
+    dst[idx[i]] = val[i];
+}
+
+cudaError_t scatter_values(const int64_t* idx_dev, const float* val_dev, int64_t nnz, float* dst_dev,
+                           cudaStream_t stream) {
+  if (nnz <= 0) return cudaSuccess;
+  int64_t grid = (nnz + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  scatter_values_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(idx_dev, val_dev, nnz, dst_dev);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,10 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
                       int64_t ldk, int64_t k_total, int64_t n, int precision,
                       cudaStream_t stream, bool keep_fp32 = false);
 
+// dst[idx[i]] = val[i]: rebuilds a mostly-zero fp32 source from its nonzeros (dst zeroed by the caller)
+cudaError_t scatter_values(const int64_t* idx_dev, const float* val_dev, int64_t nnz, float* dst_dev,
+                           cudaStream_t stream);
+
 // dst[row_map[r]] = src row r for r < rows: C back in the ORIGINAL row order (row_map = the
 // reference's get_permutation, utilities.cpp:8-20).  Both matrices have n columns and arbitrary
 // element strides (row stride sr, column stride sj).

@@ -94,7 +94,8 @@ struct PackJob {
                       // before the block: TMA needs a 16-byte aligned k coordinate)
   int32_t k_w;        // block width w: image column kk holds k = k_lo + kk iff 0 <= k < w
   uint32_t dst_off16; // destination offset, 16-byte units
-  int32_t pad_[3];
+  int32_t r_base;     // row of the image (dst_off16 = its row 0) that source row 0 goes to
+  int32_t pad_[2];
 };
 
 enum Precision : int32_t { PREC_BF16 = 0, PREC_FP16 = 1, PREC_TF32 = 2 };

@@ -17,26 +17,42 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static const char* build_structure_for(const BlockRows& br, const ScheduleOptions& opt, int64_t chain,
                                        Structure* out);
 
-// Cuts chunks [c0, c1) of the super-row starting at chunks[begin] into passes of at most `chain`
-// MMAs each (balanced; chain <= 0: one pass).  Appends the first chunk of every pass to *offs.
+// Cuts chunks [c0, c1) of the super-row starting at chunks[begin] into passes such that no
+// ACCUMULATOR receives more than `chain` MMAs in one pass (balanced; chain <= 0: one pass).  A
+// member's accumulator only takes the MMAs of the chunks it is present in, so the count is kept
+// per member: a super-row of many short, rarely overlapping block-rows needs far fewer passes than
+// its chunk count suggests.  Appends the first chunk of every pass to *offs.
 static void cut_passes(const std::vector<Chunk>& chunks, int64_t begin, int32_t c0, int32_t c1,
                        int64_t chain, std::vector<int32_t>* offs, int64_t* longest) {
-  int64_t total = 0;
-  for (int32_t c = c0; c < c1; ++c) total += chunks[begin + c].ksteps;
-  const int64_t passes = chain > 0 ? std::max<int64_t>(1, (total + chain - 1) / chain) : 1;
-  const int64_t target = (total + passes - 1) / passes;
-  int64_t run = 0;
+  int64_t total[kMaxMembers] = {0};
+  for (int32_t c = c0; c < c1; ++c) {
+    const Chunk& ch = chunks[begin + c];
+    for (uint32_t m = ch.mask; m; m &= m - 1) total[__builtin_ctz(m)] += ch.ksteps;
+  }
+  int64_t worst = 0;
+  for (int m = 0; m < kMaxMembers; ++m) worst = std::max(worst, total[m]);
+  const int64_t passes = chain > 0 ? std::max<int64_t>(1, (worst + chain - 1) / chain) : 1;
+  const int64_t target = (worst + passes - 1) / passes;
+  int64_t run[kMaxMembers] = {0};
+  int64_t run_max = 0;
   offs->push_back(c0);
   for (int32_t c = c0; c < c1; ++c) {
-    const int64_t k = chunks[begin + c].ksteps;
-    if (run > 0 && run + k > target) {
-      if (longest) *longest = std::max(*longest, run);
+    const Chunk& ch = chunks[begin + c];
+    int64_t next_max = run_max;
+    for (uint32_t m = ch.mask; m; m &= m - 1) next_max = std::max(next_max, run[__builtin_ctz(m)] + ch.ksteps);
+    if (run_max > 0 && next_max > target) {
+      if (longest) *longest = std::max(*longest, run_max);
       offs->push_back(c);
-      run = 0;
+      for (int m = 0; m < kMaxMembers; ++m) run[m] = 0;
+      run_max = 0;
     }
-    run += k;
+    for (uint32_t m = ch.mask; m; m &= m - 1) {
+      int64_t& r = run[__builtin_ctz(m)];
+      r += ch.ksteps;
+      run_max = std::max(run_max, r);
+    }
   }
-  if (longest) *longest = std::max(*longest, run);
+  if (longest) *longest = std::max(*longest, run_max);
 }
 
 // chain limit in MMAs per accumulator: tf32 sums are held to <= 1e-5, and the tensor
@@ -64,6 +80,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
   st.acc_cols = opt.acc_cols;
   st.master_col = chain > 0 ? 256 : 0;
   st.chain = chain;
+  st.sparse_images = !br.sub_ptr.empty();
   if (br.w <= 0) return "column block size must be positive";
   if (opt.seg_rows < 16 || opt.seg_rows > 256 || opt.seg_rows % 16) return "seg_rows must be a multiple of 16 in [16,256]";
   if (opt.acc_cols != 256 && opt.acc_cols != 512) return "acc_cols must be 256 or 512";
@@ -101,7 +118,14 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
     if (H <= 0) continue;
     st.rows = std::max<int64_t>(st.rows, br.row0[b] + H);
     if (br.row0[b] + H > INT32_MAX) return "shard has more than 2^31 rows";
-    if (br.blk_kw.empty()) st.nztot += nblk * H * br.w;
+    if (!br.sub_ptr.empty()) {
+      // fused block-rows: blocks and area of the ORIGINAL blocks
+      st.n_blocks -= nblk;
+      for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) {
+        st.n_blocks += br.sub_ptr[q + 1] - br.sub_ptr[q];
+        for (int64_t t = br.sub_ptr[q]; t < br.sub_ptr[q + 1]; ++t) st.nztot += br.sub_h[t] * br.w;
+      }
+    } else if (br.blk_kw.empty()) st.nztot += nblk * H * br.w;
     else for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) st.nztot += H * br.blk_kw[q];
     for (int64_t off = 0; off < H; off += opt.seg_rows) {
       Segment sg;
@@ -218,6 +242,29 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
             for (int cta = 0; cta < nshare; ++cta) {
               const int r0 = std::max(lo, cta * half), r1 = std::min(hi, (cta + 1) * half);
               if (r0 >= r1) continue;
+              if (!br.sub_ptr.empty()) {
+                // one job per sub-block that reaches into rows [r0, r1) of the run; a job writes
+                // only its own rows (the buffer is zeroed first, Structure::sparse_images)
+                const int64_t b_lo = seg_src[s].row_off + (r0 - lo), b_hi = seg_src[s].row_off + (r1 - lo);
+                for (int64_t t = br.sub_ptr[q]; t < br.sub_ptr[q + 1]; ++t) {
+                  const int64_t a = std::max(b_lo, br.sub_off[t]);
+                  const int64_t e = std::min(b_hi, br.sub_off[t] + br.sub_h[t]);
+                  if (a >= e) continue;
+                  PackJob job;
+                  job.src_rs = br.sub_rs[t];
+                  job.src_ks = br.sub_ks[t];
+                  job.src_base = br.sub_src[t] + (a - br.sub_off[t]) * job.src_rs;
+                  job.h = job.h_pad = static_cast<int32_t>(e - a);
+                  job.k_lo = static_cast<int32_t>(k_lo);
+                  job.k_w = static_cast<int32_t>(kw);
+                  job.r_base = static_cast<int32_t>(a - b_lo);
+                  job.pad_[0] = job.pad_[1] = 0;
+                  job.dst_off16 = static_cast<uint32_t>((chunk_base + cta * share + cursor[cta]) >> 4);
+                  st.jobs.push_back(job);
+                }
+                cursor[cta] += static_cast<uint32_t>(r1 - r0) * 128u;
+                continue;
+              }
               PackJob job;
               job.src_rs = br.blk_rs.empty() ? br.rs[b] : br.blk_rs[q];
               job.src_ks = br.blk_ks.empty() ? br.ks[b] : br.blk_ks[q];
@@ -226,7 +273,8 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
               job.h_pad = r1 - r0;
               job.k_lo = static_cast<int32_t>(k_lo);
               job.k_w = static_cast<int32_t>(kw);
-              job.pad_[0] = job.pad_[1] = job.pad_[2] = 0;
+              job.r_base = 0;
+              job.pad_[0] = job.pad_[1] = 0;
               job.dst_off16 = static_cast<uint32_t>((chunk_base + cta * share + cursor[cta]) >> 4);
               st.jobs.push_back(job);
               cursor[cta] += static_cast<uint32_t>(r1 - r0) * 128u;
@@ -521,6 +569,71 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
   }
   as.cta_ptr[as.workers] = static_cast<int32_t>(as.cta_items.size());
   return "";
+}
+
+bool fuse_short_block_rows(const BlockRows& in, int max_rows, BlockRows* out) {
+  if (!in.blk_k0.empty() || !in.sub_ptr.empty()) return false;
+  const int64_t nb = in.count();
+  // greedy runs of consecutive short block-rows
+  std::vector<int64_t> first;   // first block-row of every output block-row, plus nb at the end
+  bool any = false;
+  for (int64_t b = 0; b < nb;) {
+    first.push_back(b);
+    int64_t e = b + 1;
+    if (in.height[b] > 0 && in.height[b] < max_rows) {
+      int64_t rows = in.height[b];
+      while (e < nb && in.height[e] > 0 && rows + in.height[e] <= max_rows &&
+             in.row0[e] == in.row0[e - 1] + in.height[e - 1]) {
+        rows += in.height[e];
+        ++e;
+      }
+    }
+    if (e > b + 1) any = true;
+    b = e;
+  }
+  first.push_back(nb);
+  if (!any) return false;
+  BlockRows f;
+  f.w = in.w;
+  f.ptr.push_back(0);
+  f.sub_ptr.push_back(0);
+  std::vector<std::pair<int64_t, int64_t>> ent;   // (column block, source block index)
+  for (size_t g = 0; g + 1 < first.size(); ++g) {
+    const int64_t b0 = first[g], b1 = first[g + 1];
+    int64_t rows = 0;
+    ent.clear();
+    for (int64_t b = b0; b < b1; ++b) {
+      for (int64_t q = in.ptr[b]; q < in.ptr[b + 1]; ++q) ent.emplace_back(in.col[q], q);
+      rows += in.height[b];
+    }
+    f.row0.push_back(in.row0[b0]);
+    f.height.push_back(rows);
+    f.rs.push_back(in.rs[b0]);
+    f.ks.push_back(in.ks[b0]);
+    std::stable_sort(ent.begin(), ent.end());   // by column block, then by member (q ascending)
+    // row offset of every member inside the fused block-row
+    for (size_t i = 0; i < ent.size();) {
+      size_t j = i;
+      f.col.push_back(ent[i].first);
+      f.src.push_back(in.src[ent[i].second]);
+      while (j < ent.size() && ent[j].first == ent[i].first) {
+        const int64_t q = ent[j].second;
+        // the member that owns block q
+        const int64_t b = std::upper_bound(in.ptr.begin() + b0, in.ptr.begin() + b1 + 1, q) - in.ptr.begin() - 1;
+        f.sub_off.push_back(in.row0[b] - in.row0[b0]);
+        f.sub_h.push_back(in.height[b]);
+        f.sub_src.push_back(in.src[q]);
+        f.sub_rs.push_back(in.rs[b]);
+        f.sub_ks.push_back(in.ks[b]);
+        ++j;
+      }
+      f.sub_ptr.push_back(static_cast<int64_t>(f.sub_off.size()));
+      i = j;
+    }
+    f.ptr.push_back(static_cast<int64_t>(f.col.size()));
+  }
+  *out = std::move(f);
+  return true;
 }
 
 void partition_block_rows(int64_t block_rows, const int64_t* row_part, const int64_t* nzcount,

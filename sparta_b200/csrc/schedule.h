@@ -25,8 +25,27 @@ struct BlockRows {
   std::vector<int64_t> blk_kw;    // extent of the block along k (default w)
   std::vector<int64_t> blk_rs;    // element stride between rows of the block (default rs[b])
   std::vector<int64_t> blk_ks;    // element stride between k of the block (default ks[b])
+  // Optional sub-block lists (empty = every block is one sub-block covering the whole height).
+  // They describe FUSED block-rows (fuse_short_block_rows): a block of a fused block-row is the
+  // stack of the blocks its member block-rows own at that column block, each with its own source.
+  std::vector<int64_t> sub_ptr;   // [blocks + 1] ranges into the sub_* arrays
+  std::vector<int64_t> sub_off;   // first row of the sub-block inside the (fused) block-row
+  std::vector<int64_t> sub_h;     // its rows
+  std::vector<int64_t> sub_src;   // element offset of its (0,0) entry in the fp32 source
+  std::vector<int64_t> sub_rs;    // element stride between its rows
+  std::vector<int64_t> sub_ks;    // element stride between its k
   int64_t count() const { return static_cast<int64_t>(height.size()); }
 };
+
+// Variable-height blockings (-a 3/4 at low tau) produce long runs of block-rows one or two rows
+// tall; each would occupy a 16-row MMA segment of its own and walk its own column-block list.
+// This fuses runs of CONSECUTIVE block-rows (adjacent rows of C) whose heights add up to at most
+// max_rows into one block-row whose column-block list is the union of theirs; rows without a block
+// at a column block are zero rows of the image.  The device images never get larger (a union is
+// at most the sum) and usually several times smaller.  The host VBR arrays are untouched and
+// FLOPs are still counted on the original blocks.  Returns false (and leaves *out alone) when
+// there is nothing to fuse or the view already has per-block overrides.
+bool fuse_short_block_rows(const BlockRows& in, int max_rows, BlockRows* out);
 
 struct ScheduleOptions {
   int precision = PREC_BF16;
@@ -61,6 +80,7 @@ struct Structure {           // independent of the number of B columns
   int64_t  rows = 0;                 // C rows covered by the shard
   uint32_t max_chunk_bytes = 0;      // largest per-CTA chunk (what must fit in the smem ring)
   int pair = 0;
+  bool sparse_images = false;        // jobs write only their own rows: the image buffer must be zeroed first
 };
 
 // Decomposition of a chunk's member mask into MMA runs.  A run is a maximal group of

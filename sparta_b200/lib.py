@@ -28,7 +28,7 @@ class Options(C.Structure):
         ("seg_rows", C.c_int32), ("acc_cols", C.c_int32), ("panel_stages", C.c_int32),
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
         ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
-        ("max_chain", C.c_int32), ("split_k", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("max_chain", C.c_int32), ("split_k", C.c_int32), ("fuse_rows", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -325,7 +325,7 @@ ITEM_DT = np.dtype([("srow", "<i4"), ("j0", "<i4"), ("chunk_off", "<i4"), ("coun
 ITEM_NOT_FIRST, ITEM_NOT_LAST, ITEM_ATOMIC, ITEM_COUNT_MASK = 1 << 31, 1 << 30, 1 << 29, (1 << 29) - 1
 JOB_DT = np.dtype([("src_base", "<i8"), ("src_rs", "<i8"), ("src_ks", "<i8"), ("h", "<i4"),
                    ("h_pad", "<i4"), ("k_lo", "<i4"), ("k_w", "<i4"), ("dst_off16", "<u4"),
-                   ("pad", "<i4", (3,))])
+                   ("r_base", "<i4"), ("pad", "<i4", (2,))])
 ZERO_DT = np.dtype([("srow", "<i4"), ("j0", "<i4")])
 _PLAN_DTYPES = [SEG_DT, SROW_DT, CHUNK_DT, ITEM_DT, np.dtype("<i4"), np.dtype("<i4"), JOB_DT, np.dtype("<u4"), ZERO_DT]
 _PLAN_NAMES = ["segs", "srows", "chunks", "items", "cta_ptr", "cta_items", "jobs", "tables", "zero_jobs"]

@@ -24,7 +24,8 @@ def pack_images(jobs, src, a_bytes, esize):
                     k = int(job["k_lo"]) + c * epc + e
                     if r < job["h"] and 0 <= k < int(job["k_w"]):
                         vals[e] = src[int(job["src_base"]) + r * int(job["src_rs"]) + k * int(job["src_ks"])]
-                store[base16 + r * 8 + (c ^ (r & 7))] = vals
+                ro = int(job["r_base"]) + r     # row inside the image (swizzle phase follows the image)
+                store[base16 + ro * 8 + (c ^ (ro & 7))] = vals
     return store
 
 

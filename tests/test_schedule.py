@@ -84,6 +84,16 @@ def test_plan_shard_range(lib, oracle):
     assert np.array_equal(np.concatenate(pieces, axis=1), Cref)
 
 
+def _longest_chain(chunks, srows, it):
+    """MMAs the pass `it` issues into the busiest accumulator: a member's accumulator only takes
+    the MMAs of the chunks it is present in (cut_passes, csrc/schedule.cpp)."""
+    c0 = int(srows[it["srow"]]["chunk_begin"] + it["chunk_off"])
+    cnt = int(it["count"]) & sparta_b200.lib.ITEM_COUNT_MASK
+    ch = chunks[c0:c0 + cnt]
+    per_member = [int(ch["ksteps"][(ch["mask"] >> m) & 1 == 1].sum()) for m in range(32)]
+    return max(per_member) if cnt else 0
+
+
 @pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
 @pytest.mark.parametrize("precision,esize,max_chain", [("tf32", 4, 8), ("tf32", 4, 24), ("bf16", 2, 16), ("tf32", 4, 0)])
 def test_bounded_accumulation_chains(oracle, lib, precision, esize, max_chain, pair):
@@ -106,9 +116,7 @@ def test_bounded_accumulation_chains(oracle, lib, precision, esize, max_chain, p
     else:
         assert not multi.any()                       # 32 blocks x 8 MMAs = 256: fits the default
     for it in items:
-        c0 = srows[it["srow"]]["chunk_begin"] + it["chunk_off"]
-        n_mma = int(chunks["ksteps"][c0:c0 + (int(it["count"]) & sparta_b200.lib.ITEM_COUNT_MASK)].sum())
-        assert n_mma <= limit
+        assert _longest_chain(chunks, srows, it) <= limit
     assert count.sum() == sum(int(sr["chunk_count"]) for sr in srows) * len(np.unique(items["j0"]))
     Cm = sched_interp.run_plan(plan, v["mab"], Bm, 2048, n, v["rows"], esize=esize)
     assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
@@ -145,9 +153,7 @@ def test_split_pieces_cover_every_chunk_once(oracle, lib, precision, esize, max_
     assert atomic.sum() == st["split_pieces"]
     if max_chain:
         for it in plan["items"]:
-            c0 = plan["srows"][it["srow"]]["chunk_begin"] + it["chunk_off"]
-            cnt = int(it["count"]) & sparta_b200.lib.ITEM_COUNT_MASK
-            assert int(plan["chunks"]["ksteps"][c0:c0 + cnt].sum()) <= max_chain
+            assert _longest_chain(plan["chunks"], plan["srows"], it) <= max_chain
     Cm = sched_interp.run_plan(plan, v["mab"], Bm, 4096, n, v["rows"], esize=esize)
     assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
 
@@ -229,3 +235,31 @@ def test_modelled_partition_is_contiguous_and_no_worse_than_area(lib):
                 t.append(p["stats"]["sched_max_cycles"])
             return max(t)
         assert worst(model) <= worst(area) * 1.001
+
+
+@pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
+@pytest.mark.parametrize("precision,esize", [("bf16", 2), ("tf32", 4)])
+def test_fused_short_block_rows(oracle, lib, precision, esize, pair):
+    """Runs of consecutive short block-rows share one 16-row segment with the union of their
+    column-block lists (fuse_short_block_rows): same product, same nztot / block count as the
+    original VBR, fewer segments and no more image bytes than the unfused plan."""
+    rng = np.random.default_rng(81)
+    heights = [1, 1, 2, 1, 5, 1, 1, 1, 1, 3, 64, 1, 1, 1, 9, 8, 1, 1, 40, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2]
+    v = random_vbr(rng, len(heights), 640, 32, heights, 0.35, values="int")
+    n = 70
+    Bm = rng.integers(-3, 4, size=(n, 640)).astype(np.float32)
+    fused = sparta_b200.vbr_plan(v["rows"], 640, 32, v["row_part"], v["nzcount"], v["jab"], n,
+                                 precision=precision, cta_pair=pair)
+    plain = sparta_b200.vbr_plan(v["rows"], 640, 32, v["row_part"], v["nzcount"], v["jab"], n,
+                                 precision=precision, cta_pair=pair, fuse_rows=1)
+    for p in (fused, plain):
+        assert p["stats"]["nztot"] == v["mab"].size and p["stats"]["nz_blocks"] == v["jab"].size
+        assert p["segs"]["h"].sum() == v["rows"]
+    assert len(fused["segs"]) < len(plain["segs"]) == len(heights)        # every block-row here fits one segment
+    assert fused["stats"]["a_packed_bytes"] <= plain["stats"]["a_packed_bytes"]
+    assert fused["stats"]["chunks"] < plain["stats"]["chunks"]
+    assert np.any(fused["jobs"]["r_base"] > 0)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    for p in (fused, plain):
+        Cm = sched_interp.run_plan(p, v["mab"], Bm, 640, n, v["rows"], esize=esize)
+        assert not np.isnan(Cm).any() and np.array_equal(Cm, Cref)
