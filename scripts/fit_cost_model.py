@@ -23,11 +23,15 @@ def main():
     idx = np.load(sys.argv[2])          # row_part / nzcount / jab of the workload
     rp, nz, jab = idx["row_part"], idx["nzcount"], idx["jab"]
     n, cols, w = int(sys.argv[3]) if len(sys.argv) > 3 else 2048, 65536, 64
+    partition = sys.argv[4] if len(sys.argv) > 4 else "area"
     clock = 1.965e9
     X, y, tag = [], [], []
     for rec in res:
         world = rec["world"]
-        cuts = sparta_b200.partition_block_rows(rp, nz, world)
+        if partition == "model":
+            cuts = sparta_b200.partition_block_rows_modelled(int(rp[-1]), cols, w, rp, nz, jab, n, world, split_k=rec["split_k"])
+        else:
+            cuts = sparta_b200.partition_block_rows(rp, nz, world)
         for pr in rec["per_rank"]:
             r = pr["rank"]
             plan = L.vbr_plan(int(rp[-1]), cols, w, rp, nz, jab, n, block_row_begin=int(cuts[r]),
@@ -49,6 +53,10 @@ def main():
             y.append(pr["ms"] * 1e-3 * clock)
             tag.append((rec["split_k"], world, r))
     X, y = np.array(X), np.array(y)
+    Xi = np.concatenate([np.ones((len(X), 1)), X], axis=1)
+    ci, *_ = np.linalg.lstsq(Xi, y, rcond=None)
+    print(f"with intercept: cycles ~ {ci[0]:.0f} + {ci[1]:.0f}*items + {ci[2]:.1f}*chunks + {ci[3]:.3f}*rows   "
+          f"median |err| {np.median(np.abs(Xi @ ci - y) / y):.3f}, max {np.max(np.abs(Xi @ ci - y) / y):.3f}")
     for sel, name in ((np.array([t[0] == 0 for t in tag]), "split plans"), (np.ones(len(tag), bool), "all plans")):
         coef, *_ = np.linalg.lstsq(X[sel], y[sel], rcond=None)
         pred = X[sel] @ coef

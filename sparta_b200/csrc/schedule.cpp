@@ -182,7 +182,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
     // Per work item: draining the accumulator (measured 20.4 k cycles for 512 columns while the
     // other SMs keep the L2 busy; the stores, not the TMEM reads, are the limit -- see
     // scripts/microbench/epilogue_rate.cu) plus the tensor pipe running dry and refilling.
-    const double fixed = 10000.0 + 40.0 * cols;
+    const double fixed = 16000.0 + 40.0 * cols;
     double cost = fixed;
     size_t i = 0;
     while (i < merged.size()) {
@@ -292,10 +292,11 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         st.max_chunk_bytes = std::max(st.max_chunk_bytes, share);
         st.chunks.push_back(ch);
         // modelled cycles per CTA: tensor pipe N/2 per K step; L2 -> smem: fitted to the kernel
-        // times of 29 shards of the bench matrix (scripts/fit_cost_model.py): 490 cycles per chunk
-        // + 1.27 per staged row of A in pair mode (64 bytes per row and CTA => ~50 B/cycle/SM)
+        // times of 30 shards of the bench matrix (scripts/fit_cost_model.py): 511 cycles per chunk
+        // + 1.25 per staged row of A in pair mode (64 bytes per row and CTA => ~50 B/cycle/SM),
+        // 36.7 k per item
         const double tensor = ch.ksteps * (rows_present * 0.5);
-        const double memory = 160.0 + (kPanelBytes + share) / 50.0;
+        const double memory = 183.0 + (kPanelBytes + share) / 50.0;
         st.chunk_cost.push_back(static_cast<float>(std::max(tensor, memory)));
         cost += st.chunk_cost.back();
       }
