@@ -11,9 +11,15 @@ import numpy as np
 from . import lib as _lib
 
 
-def shard_range(row_part, nzcount, world_size, rank):
-    """Contiguous block-row range [lo, hi) of `rank`, balanced on nonzero-block area."""
-    cuts = _lib.partition_block_rows(row_part, nzcount, world_size)
+def shard_range(row_part, nzcount, world_size, rank, jab=None, cols=None, block_col_size=None, n=None, **opts):
+    """Contiguous block-row range [lo, hi) of `rank`.  With the column-block lists (`jab`, plus
+    cols / block_col_size / the number of B columns n) the ranges are balanced on the scheduler's
+    modelled kernel time per shard; without them on nonzero-block area."""
+    if jab is not None:
+        cuts = _lib.partition_block_rows_modelled(int(row_part[-1]), cols, block_col_size, row_part, nzcount, jab,
+                                                  n, world_size, **opts)
+    else:
+        cuts = _lib.partition_block_rows(row_part, nzcount, world_size)
     return int(cuts[rank]), int(cuts[rank + 1]), cuts
 
 

@@ -26,7 +26,11 @@ def _worker(rank, world, port, out_dir):
     v = random_vbr(rng, 23, 300, 32, heights, 0.4, values="int")
     n = 17
     Bm = rng.integers(-3, 4, size=(n, 300)).astype(np.float32) if rank == 0 else None
-    lo, hi, cuts = sd.shard_range(v["row_part"], v["nzcount"], world, rank)
+    if os.environ.get("SPARTA_TEST_PARTITION") == "model":
+        lo, hi, cuts = sd.shard_range(v["row_part"], v["nzcount"], world, rank, jab=v["jab"], cols=300,
+                                      block_col_size=32, n=n)
+    else:
+        lo, hi, cuts = sd.shard_range(v["row_part"], v["nzcount"], world, rank)
     assert cuts[0] == 0 and cuts[-1] == 23 and np.all(np.diff(cuts) >= 0)
     Bd = sd.broadcast_B(Bm, (n, 300), torch.device("cpu"))
     # the shard's product (stand-in for the CUDA kernel on this CPU box)
@@ -45,8 +49,13 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_broadcast_gather(tmp_path, oracle):
-    port = 29500 + os.getpid() % 2000
+import pytest
+
+
+@pytest.mark.parametrize("partition", ["area", "model"])
+def test_two_rank_shard_broadcast_gather(tmp_path, oracle, partition, monkeypatch):
+    monkeypatch.setenv("SPARTA_TEST_PARTITION", partition)
+    port = 29500 + (os.getpid() + (7 if partition == "model" else 0)) % 2000
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(tmp_path / f"rank{r}.txt").read() == "ok"

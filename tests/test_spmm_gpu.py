@@ -526,3 +526,35 @@ def test_sparse_upload_matches_dense_upload(oracle, lib, monkeypatch):
     monkeypatch.setenv("SPARTA_DENSE_UPLOAD", "1")
     dense = gpu_multiply(v, Bm, n, "bf16")
     assert np.array_equal(sparse, Cref) and np.array_equal(dense, Cref)
+
+
+def test_shards_scatter_into_one_matrix_in_original_order(oracle, lib):
+    """Multi-GPU read-back on one device: every shard scatters its slab of C straight into a
+    full-size DEVICE matrix in the original row order (sparta_get_C_permuted, on_device = 1)."""
+    import ctypes as C
+    import torch
+    from sparta_b200 import lib as L
+    from sparta_b200.lib import host_permutation
+    res = oracle.run(os.path.join(GOLDEN, "rmat8.el"), P=1, a=5, b=16, B=16, t=0.6)
+    rows = res["rows"]
+    perm = host_permutation(res["grouping"])
+    rng = np.random.default_rng(52)
+    n = 40
+    Bm = rng.integers(-3, 4, size=(n, rows)).astype(np.float32)
+    Cref = oracle.csr_multiply(rows, res["csr_rowptr"], res["csr_colind"], res["csr_val"], True, Bm, n)
+    full = torch.full((n, rows), -1.0, dtype=torch.float32, device="cuda")
+    cuts = sparta_b200.partition_block_rows_modelled(rows, res["cols"], 16, res["row_part"], res["nzcount"], res["jab"], n, 3)
+    for i in range(3):
+        lo, hi = int(cuts[i]), int(cuts[i + 1])
+        h = sparta_b200.Handle.from_vbr(rows, res["cols"], 16, res["row_part"], res["nzcount"], res["jab"], res["mab"],
+                                        block_row_begin=lo, block_row_end=hi)
+        h.set_B(Bm, rows, n)
+        h.run()
+        r0, r1 = int(res["row_part"][lo]), int(res["row_part"][hi])
+        row_map = np.ascontiguousarray(perm[r0:r1], dtype=np.int64)
+        if r1 > r0:
+            L._check(sparta_b200.load().sparta_get_C_permuted(h._h, C.c_void_p(full.data_ptr()), rows, L._ptr(row_map),
+                                                              rows, 1))
+        h.close()
+    torch.cuda.synchronize()
+    assert np.array_equal(full.cpu().numpy(), Cref)
