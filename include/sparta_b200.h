@@ -62,7 +62,7 @@ typedef struct sparta_options {
   int32_t l2_slab_mb;    /* B columns walked per pass over A, in MiB of B (default 160) */
   int32_t max_chain;     /* longest run of tcgen05.mma accumulations into one TMEM accumulator before the
                             partial sum is drained and added to C in fp32 by the epilogue; 0 = the
-                            precision's default (tf32: 128, bf16/fp16: unlimited), -1 = unlimited */
+                            precision's default (tf32: 256 per accumulator, bf16/fp16: unlimited), -1 = unlimited */
   int32_t split_k;       /* few super-rows per worker (small shards): cut the block-rows' column-block
                             lists into equal-cost pieces, one per worker, partial sums added to C with
                             fp32 reductions.  0: when the cost model says it pays (default), 1: never,

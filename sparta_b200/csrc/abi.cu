@@ -443,6 +443,8 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
       cudaStreamSynchronize(h->stream);                                        \
       if (d_src) cudaFreeAsync(d_src, h->stream);                              \
       if (d_jobs) cudaFreeAsync(d_jobs, h->stream);                            \
+      if (d_idx) cudaFreeAsync(d_idx, h->stream);                              \
+      if (d_val) cudaFreeAsync(d_val, h->stream);                              \
       free_handle(h);                                                          \
       return fail_cuda(e_, #call);                                             \
     }                                                                          \
@@ -450,6 +452,8 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
 
   float* d_src = nullptr;
   PackJob* d_jobs = nullptr;
+  int64_t* d_idx = nullptr;   // nonzeros-only upload
+  float* d_val = nullptr;
   H_TRY(cudaEventRecord(h->up0, h->stream));
   bool sparse_upload = false;
   if (src_elems > 0) {
@@ -463,8 +467,6 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
     if (src_elems >= (int64_t{1} << 22) && !getenv("SPARTA_DENSE_UPLOAD") &&
         sampled_density(src_host, src_elems) < 0.10 && scan_nonzeros(src_host, src_elems, &sp)) {
       sparse_upload = true;
-      int64_t* d_idx = nullptr;
-      float* d_val = nullptr;
       const int64_t nnz = sp.total;
       H_TRY(cudaMemsetAsync(d_src, 0, static_cast<size_t>(src_elems) * sizeof(float), h->stream));
       if (nnz > 0) {
@@ -482,6 +484,8 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
         // pageable sources are staged before cudaMemcpyAsync returns; the vectors may go away
         dev_free(d_idx, h->stream);
         dev_free(d_val, h->stream);
+        d_idx = nullptr;
+        d_val = nullptr;
       }
     } else {
       H_TRY(cudaMemcpyAsync(d_src, src_host, static_cast<size_t>(src_elems) * sizeof(float),
@@ -506,7 +510,8 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   if (h->st.sparse_images && h->st.a_bytes) H_TRY(cudaMemsetAsync(h->d_a, 0, h->st.a_bytes, h->stream));
   if (!h->st.jobs.empty()) {
     H_TRY(upload_vec(h->st.jobs, &d_jobs, h->stream));
-    H_TRY(pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream));
+    H_TRY(pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream,
+                        static_cast<int64_t>(h->st.a_bytes)));
   }
   dev_free(d_src, h->stream);
   dev_free(d_jobs, h->stream);

@@ -30,6 +30,39 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, int precision) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// One CTA per job: the right shape when an image is tens of rows (64x64 blocks: 256 items of work).
+__global__ void __launch_bounds__(256) pack_a_images_cta_kernel(const float* __restrict__ src,
+                                                                const PackJob* __restrict__ jobs,
+                                                                uint8_t* __restrict__ dst,
+                                                                int precision) {
+  const PackJob job = jobs[blockIdx.x];
+  const int epc = (precision == PREC_TF32) ? 4 : 8;  // elements per 16-byte chunk
+  uint8_t* out = dst + static_cast<size_t>(job.dst_off16) * 16;
+  const int total = job.h_pad * 8;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx % job.h_pad;
+    const int c = idx / job.h_pad;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = job.k_lo + c * epc + e;   // block-local k
+      v[e] = (e < epc && r < job.h && k >= 0 && k < job.k_w)
+                 ? src[job.src_base + static_cast<int64_t>(r) * job.src_rs +
+                       static_cast<int64_t>(k) * job.src_ks]
+                 : 0.f;
+    }
+    uint4 o;
+    if (precision == PREC_TF32) {
+      o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+    } else {
+      o = make_uint4(pack2(v[0], v[1], precision), pack2(v[2], v[3], precision),
+                     pack2(v[4], v[5], precision), pack2(v[6], v[7], precision));
+    }
+    const int ro = job.r_base + r;   // row inside the image
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(ro) * 128 + ((c ^ (ro & 7)) << 4)) = o;
+  }
+}
+
 // One WARP per job (8 jobs per CTA): fused short block-rows produce millions of jobs of a row or
 // two, for which a CTA per job spent a second launching blocks.  Lane t walks (row r fastest,
 // 16-byte chunk c) so that column-major sources are read coalesced along r.
@@ -118,13 +151,19 @@ __global__ void convert_b_rowmajor_kernel(const float* __restrict__ src, int64_t
 }
 
 cudaError_t pack_a_images(const float* src_dev, const PackJob* jobs_dev, int64_t n_jobs,
-                          uint8_t* dst_dev, int precision, cudaStream_t stream) {
+                          uint8_t* dst_dev, int precision, cudaStream_t stream, int64_t image_bytes) {
+  // mean work per job in 16-byte pieces decides between a CTA and a warp per job
+  const bool small_jobs = image_bytes > 0 && image_bytes / 16 / (n_jobs > 0 ? n_jobs : 1) < 128;
   // gridDim.x limit is 2^31-1; stay well below it per launch anyway
   const int64_t kMaxGrid = 1 << 30;
   for (int64_t done = 0; done < n_jobs; done += kMaxGrid) {
     const int64_t g = (n_jobs - done < kMaxGrid) ? (n_jobs - done) : kMaxGrid;
-    pack_a_images_kernel<<<static_cast<unsigned>((g + 7) / 8), 256, 0, stream>>>(src_dev, jobs_dev + done, g,
-                                                                                dst_dev, precision);
+    if (small_jobs)
+      pack_a_images_kernel<<<static_cast<unsigned>((g + 7) / 8), 256, 0, stream>>>(src_dev, jobs_dev + done, g,
+                                                                                  dst_dev, precision);
+    else
+      pack_a_images_cta_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(src_dev, jobs_dev + done, dst_dev,
+                                                                            precision);
   }
   return cudaGetLastError();
 }

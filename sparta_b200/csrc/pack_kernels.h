@@ -5,8 +5,9 @@
 
 namespace sparta {
 
+// image_bytes: total bytes of the images the jobs write (0 if unknown)
 cudaError_t pack_a_images(const float* src_dev, const PackJob* jobs_dev, int64_t n_jobs,
-                          uint8_t* dst_dev, int precision, cudaStream_t stream);
+                          uint8_t* dst_dev, int precision, cudaStream_t stream, int64_t image_bytes = 0);
 
 cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void* dst_dev,
                       int64_t ldk, int64_t k_total, int64_t n, int precision,
