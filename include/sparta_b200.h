@@ -159,7 +159,10 @@ int sparta_set_C(sparta_handle* h, const float* C, int64_t ld, int on_device);
 /* One multiply on the handle's stream.  *dt_ms (may be NULL) = CUDA-event time
  * around the compute kernel only, like the reference's dt (cuda_utilities.cpp:139,186-189). */
 int sparta_run(sparta_handle* h, float* dt_ms);
-/* Enqueue without timing or synchronisation (for CUDA-graph / external event timing). */
+/* Enqueue without timing or synchronisation (for external event timing / stream capture).
+ * A handle whose plan has split pieces (sparta_stats.split_pieces > 0) passes a per-launch counter
+ * target to the kernel, so a CAPTURED launch of it must not be replayed: create the handle with
+ * split_k = 1 if the launch is to live in a CUDA graph. */
 int sparta_run_async(sparta_handle* h);
 int sparta_synchronize(sparta_handle* h);
 
