@@ -338,6 +338,7 @@ struct TeamPiece { int32_t group, srow, c0, c1; bool partial; };
 
 struct TeamPlan {
   int workers = 0, team = 1;
+  int spare = 0;   // width of one extra, narrower team made of the workers a multiple of `team` leaves over
   std::vector<std::vector<TeamPiece>> per_team;
   double max_cost = 0, mean_cost = 0;
   int cut_units = 0;
@@ -365,8 +366,14 @@ void finish_costs(TeamPlan* tp, const std::vector<double>& load) {
   tp->mean_cost = load.empty() ? 0.0 : total / load.size();
 }
 
+// The workers a multiple of the team width leaves over (74 CTA pairs = 9 teams of 8 + 2) form one
+// narrower team: its members take the column tiles of a group in turns (4 each for 2 members of
+// an 8-tile group), so a unit costs it team / spare times as much and the list scheduler gives it
+// proportionally fewer units.
 void plan_whole(const Structure& st, const std::vector<int32_t>& by_cost, int64_t groups, TeamPlan* tp) {
-  const int n_teams = tp->workers / tp->team;
+  const int n_full = tp->workers / tp->team;
+  const int n_teams = n_full + (tp->spare > 0 ? 1 : 0);
+  const double spare_factor = tp->spare > 0 ? static_cast<double>(tp->team) / tp->spare : 1.0;
   tp->per_team.assign(n_teams, {});
   typedef std::pair<double, int> Load;
   std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
@@ -375,8 +382,22 @@ void plan_whole(const Structure& st, const std::vector<int32_t>& by_cost, int64_
     for (int32_t s : by_cost) {
       Load l = heap.top();
       heap.pop();
+      const double unit = st.srow_cost[s] * (l.second >= n_full ? spare_factor : 1.0);
+      if (l.second >= n_full) {
+        // would the narrow team finish this unit later than a full team could?  then pass
+        Load alt = heap.top();
+        if (alt.first + st.srow_cost[s] < l.first + unit) {
+          heap.pop();
+          heap.push(l);
+          l = alt;
+          tp->per_team[l.second].push_back({static_cast<int32_t>(g), s, 0, st.srows[s].chunk_count, false});
+          l.first += st.srow_cost[s];
+          heap.push(l);
+          continue;
+        }
+      }
       tp->per_team[l.second].push_back({static_cast<int32_t>(g), s, 0, st.srows[s].chunk_count, false});
-      l.first += st.srow_cost[s];
+      l.first += unit;
       heap.push(l);
     }
   std::vector<double> load;
@@ -513,7 +534,13 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
 
   TeamPlan whole, split;
   whole.workers = static_cast<int>(std::min<int64_t>(all_workers, static_cast<int64_t>(by_cost.size()) * tiles));
-  whole.team = pick_team(&whole.workers, tiles, fit_whole);
+  {
+    const int before = whole.workers;
+    whole.team = pick_team(&whole.workers, tiles, fit_whole);
+    // leftover workers: one narrower team whose width divides the team width
+    for (int w2 = before - whole.workers; w2 >= 1; --w2)
+      if (whole.team % w2 == 0) { whole.spare = w2; break; }
+  }
   plan_whole(st, by_cost, (tiles + whole.team - 1) / whole.team, &whole);
   const TeamPlan* tp = &whole;
   if (opt.split != 1) {
@@ -527,15 +554,18 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
     if (opt.split == 2 || pays) tp = &split;
   }
 
-  as.workers = tp->workers;
+  as.workers = tp->workers + tp->spare;
   as.team = as.group_tiles = tp->team;
   as.grid = as.workers * (st.pair ? 2 : 1);
   as.max_cta_cost = tp->max_cost;
   as.mean_cta_cost = tp->mean_cost;
   std::vector<std::vector<int32_t>> per_worker(as.workers);
   std::vector<int32_t> offs;
+  const size_t n_full_teams = static_cast<size_t>(tp->workers / tp->team);
   for (size_t t = 0; t < tp->per_team.size(); ++t)
     for (const TeamPiece& pc : tp->per_team[t]) {
+      const int width = t < n_full_teams ? tp->team : tp->spare;      // members of this team
+      const size_t team_base = (t < n_full_teams ? t : n_full_teams) * static_cast<size_t>(tp->team);
       const int64_t t0 = static_cast<int64_t>(pc.group) * tp->team;
       const int in_group = static_cast<int>(std::min<int64_t>(tp->team, tiles - t0));
       offs.clear();
@@ -553,7 +583,7 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
           if (ps > 0) count |= kItemNotFirst;
           if (ps + 1 < offs.size()) count |= kItemNotLast;
           else if (pc.partial) count |= kItemAtomic;
-          per_worker[t * tp->team + m].push_back(static_cast<int32_t>(as.items.size()));
+          per_worker[team_base + m % width].push_back(static_cast<int32_t>(as.items.size()));
           as.items.push_back(Item{pc.srow, j0, off, count});
         }
         if (pc.partial) {

@@ -263,3 +263,25 @@ def test_fused_short_block_rows(oracle, lib, precision, esize, pair):
     for p in (fused, plain):
         Cm = sched_interp.run_plan(p, v["mab"], Bm, 640, n, v["rows"], esize=esize)
         assert not np.isnan(Cm).any() and np.array_equal(Cm, Cref)
+
+
+@pytest.mark.parametrize("n,num_ctas,expect", [(1024, 12, (4, 2)), (700, 16, (3, 1)), (1024, 20, (4, 2))])
+def test_leftover_workers_form_a_narrow_team(oracle, lib, n, num_ctas, expect):
+    """Whole-unit plans: the CTA pairs a multiple of the team width leaves over work as one
+    narrower team whose members take a group's column tiles in turns.  Every (super-row, tile) is
+    still covered exactly once (checked by the interpreter) and the narrow team gets less work."""
+    rng = np.random.default_rng(95)
+    v = random_vbr(rng, 48, 1024, 64, [64] * 48, 0.5, values="int")
+    Bm = rng.integers(-3, 4, size=(n, 1024)).astype(np.float32)
+    plan = sparta_b200.vbr_plan(v["rows"], 1024, 64, v["row_part"], v["nzcount"], v["jab"], n,
+                                num_ctas=num_ctas, split_k=1)
+    team, spare = expect
+    workers = num_ctas // 2
+    assert plan["stats"]["team"] == team and plan["stats"]["grid"] == 2 * (workers // team * team + spare)
+    items_per_worker = np.diff(plan["cta_ptr"])
+    assert items_per_worker[-1] > 0                                 # the narrow team has work ...
+    cnt = plan["items"]["count"] & sparta_b200.lib.ITEM_COUNT_MASK
+    load = [int(cnt[plan["cta_items"][plan["cta_ptr"][w]:plan["cta_ptr"][w + 1]]].sum()) for w in range(len(items_per_worker))]
+    assert max(load) <= 1.35 * np.mean(load)                         # ... and is not the straggler
+    Cm = sched_interp.run_plan(plan, v["mab"], Bm, 1024, n, v["rows"])
+    assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
