@@ -409,8 +409,11 @@ void plan_whole(const Structure& st, const std::vector<int32_t>& by_cost, int64_
 // cycles; a super-row that does not fit is cut at the chunk where the team is full.  The last
 // team takes whatever is left.
 void fill_split(const Structure& st, const std::vector<int32_t>& by_cost, const std::vector<double>& prefix,
-                int n_teams, double target, std::vector<std::vector<TeamPiece>>* per_team,
+                const std::vector<double>& slow, double target, std::vector<std::vector<TeamPiece>>* per_team,
                 std::vector<double>* load) {
+  // slow[t]: how many times longer team t takes for the same piece (1 for a full team, team / spare
+  // for the narrow team of leftover workers); loads and the target are times
+  const int n_teams = static_cast<int>(slow.size());
   const int32_t kMinChunks = 8;        // never cut off a piece shorter than this
   per_team->assign(n_teams, {});
   load->assign(n_teams, 0.0);
@@ -421,16 +424,16 @@ void fill_split(const Structure& st, const std::vector<int32_t>& by_cost, const 
     const double fixed = st.srow_fixed[s];
     int32_t c = 0;
     if (sr.chunk_count == 0) {   // no blocks at all: the item only writes zeros
-      if (t < n_teams - 1 && (*load)[t] + fixed > target) ++t;
+      if (t < n_teams - 1 && (*load)[t] + fixed * slow[t] > target) ++t;
       (*per_team)[t].push_back({0, s, 0, 0, false});
-      (*load)[t] += fixed;
+      (*load)[t] += fixed * slow[t];
     }
     while (c < sr.chunk_count) {
       const double rest = pf[sr.chunk_count] - pf[c];
-      const double room = target - (*load)[t] - fixed;
+      const double room = (target - (*load)[t]) / slow[t] - fixed;
       if (t == n_teams - 1 || rest <= room) {
         (*per_team)[t].push_back({0, s, c, sr.chunk_count, false});
-        (*load)[t] += fixed + rest;
+        (*load)[t] += (fixed + rest) * slow[t];
         break;
       }
       // largest e with cost of [c, e) <= room
@@ -438,7 +441,7 @@ void fill_split(const Structure& st, const std::vector<int32_t>& by_cost, const 
           std::upper_bound(pf + c, pf + sr.chunk_count + 1, pf[c] + std::max(room, 0.0)) - pf) - 1;
       if (e - c >= kMinChunks && sr.chunk_count - e >= kMinChunks) {
         (*per_team)[t].push_back({0, s, c, e, true});
-        (*load)[t] += fixed + (pf[e] - pf[c]);
+        (*load)[t] += (fixed + (pf[e] - pf[c])) * slow[t];
         c = e;
       }
       ++t;   // this team is full (or cannot take a piece worth cutting)
@@ -453,9 +456,14 @@ void fill_split(const Structure& st, const std::vector<int32_t>& by_cost, const 
 // the same group at the same time and its B slab stays L2-resident (cutting the concatenation of
 // all groups instead put the teams in different groups: measured 30 % slower at 2 shards, the B
 // panels came from HBM).  Odd groups hand the pieces out in reverse team order to even out what
-// the greedy fill leaves to the last team.
+// the greedy fill leaves to the last team.  The workers a multiple of the team width leaves over
+// form one narrower team (always the last one) that gets proportionally shorter pieces.
 void plan_split(const Structure& st, const std::vector<int32_t>& by_cost, int64_t groups, TeamPlan* tp) {
-  const int n_teams = tp->workers / tp->team;
+  const int n_full = tp->workers / tp->team;
+  const int n_teams = n_full + (tp->spare > 0 ? 1 : 0);
+  const double factor = tp->spare > 0 ? static_cast<double>(tp->team) / tp->spare : 1.0;
+  std::vector<double> slow_fwd(n_teams, 1.0), slow_rev(n_teams, 1.0);
+  if (tp->spare > 0) { slow_fwd[n_teams - 1] = factor; slow_rev[0] = factor; }
   std::vector<double> prefix(st.chunk_cost.size() + 1, 0.0);
   for (size_t c = 0; c < st.chunk_cost.size(); ++c) prefix[c + 1] = prefix[c] + st.chunk_cost[c];
   double total = 0, biggest = 0;
@@ -463,32 +471,42 @@ void plan_split(const Structure& st, const std::vector<int32_t>& by_cost, int64_
   // Every cut re-pays the fixed part of the unit it cuts and pieces have a minimum length, so the
   // load the greedy fill ends up with is not a monotone function of the target: scan a ladder of
   // targets from the ideal mean upwards and keep the fill with the smallest maximum load.
-  const double lo = total / n_teams, hi = std::max(2.0 * lo, lo + biggest);
-  std::vector<std::vector<TeamPiece>> best, cur;
-  std::vector<double> best_load, cur_load;
-  double best_worst = 0;
-  for (double target = lo; ; target *= 1.01) {
-    const bool last = target >= hi;
-    fill_split(st, by_cost, prefix, n_teams, last ? hi : target, &cur, &cur_load);
-    const double worst = *std::max_element(cur_load.begin(), cur_load.end());
-    if (best.empty() || worst < best_worst) {
-      best.swap(cur);
-      best_load.swap(cur_load);
-      best_worst = worst;
+  const double lo = total / (n_full + (tp->spare > 0 ? 1.0 / factor : 0.0));
+  const double hi = std::max(2.0 * lo, lo + biggest * factor);
+  std::vector<std::vector<TeamPiece>> best[2], cur;
+  std::vector<double> best_load[2], cur_load;
+  double best_worst[2] = {0, 0};
+  for (int dir = 0; dir < 2; ++dir) {
+    const std::vector<double>& slow = dir ? slow_rev : slow_fwd;
+    for (double target = lo; ; target *= 1.01) {
+      const bool last = target >= hi;
+      fill_split(st, by_cost, prefix, slow, last ? hi : target, &cur, &cur_load);
+      const double worst = *std::max_element(cur_load.begin(), cur_load.end());
+      if (best[dir].empty() || worst < best_worst[dir]) {
+        best[dir].swap(cur);
+        best_load[dir].swap(cur_load);
+        best_worst[dir] = worst;
+      }
+      if (last) break;
     }
-    if (last) break;
+    if (tp->spare == 0) {   // symmetric: the reverse fill is the same lists
+      best[1] = best[0];
+      best_load[1] = best_load[0];
+      break;
+    }
   }
   tp->per_team.assign(n_teams, {});
   std::vector<double> load(n_teams, 0.0);
   for (int64_t g = 0; g < groups; ++g)
     for (int t = 0; t < n_teams; ++t) {
-      const int src = (g & 1) ? n_teams - 1 - t : t;
-      for (TeamPiece pc : best[src]) {
+      const int dir = static_cast<int>(g & 1);
+      const int src = dir ? n_teams - 1 - t : t;
+      for (TeamPiece pc : best[dir][src]) {
         pc.group = static_cast<int32_t>(g);
         tp->per_team[t].push_back(pc);
         if (pc.partial && pc.c0 == 0) ++tp->cut_units;
       }
-      load[t] += best_load[src];
+      load[t] += best_load[dir][src];
     }
   finish_costs(tp, load);
 }
@@ -548,7 +566,12 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
     for (const SuperRow& sr : st.srows) n_chunks += sr.chunk_count;
     // no more workers than pieces of >= 16 chunks
     split.workers = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(all_workers, n_chunks * tiles / 16)));
-    split.team = pick_team(&split.workers, tiles, fit);
+    {
+      const int before = split.workers;
+      split.team = pick_team(&split.workers, tiles, fit);
+      for (int w2 = before - split.workers; w2 >= 1; --w2)
+        if (split.team % w2 == 0) { split.spare = w2; break; }
+    }
     plan_split(st, by_cost, (tiles + split.team - 1) / split.team, &split);
     const bool pays = split.max_cost < 0.95 * whole.max_cost;   // the worker that finishes last sets the time
     if (opt.split == 2 || pays) tp = &split;

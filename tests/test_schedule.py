@@ -165,9 +165,9 @@ def test_split_is_chosen_only_when_it_pays(lib):
     few = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048)
     never = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048, split_k=1)
     assert few["stats"]["split_pieces"] > 0 and never["stats"]["split_pieces"] == 0
-    # whole units keep 24 of the 74 CTA pairs busy; the split plan fills the grid evenly (teams of
-    # 8 column tiles: 72 of the 74 pairs)
-    assert never["stats"]["grid"] == 48 and few["stats"]["grid"] == 144 and few["stats"]["team"] == 8
+    # whole units keep 24 of the 74 CTA pairs busy; the split plan fills the grid evenly (9 teams of
+    # 8 column tiles and the 2 leftover pairs as a narrow tenth team)
+    assert never["stats"]["grid"] == 48 and few["stats"]["grid"] == 148 and few["stats"]["team"] == 8
     assert few["stats"]["sched_imbalance"] < 1.25
     # many units per worker: list scheduling is already balanced, nothing is split
     v = random_vbr(rng, 400, 1024, 64, [64] * 400, 0.3, values="int")
