@@ -396,7 +396,13 @@ def run_ours(args, wl):
     # ---- e2e: the one-shot reference-facing call, host buffers in and out (rank-local shard)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist if world > 1 else None, total_flops)
+        rows_shard = int(v["row_part"][hi] - v["row_part"][lo])
+        c_resident = None
+        if rows_shard:
+            c_resident = np.zeros((n, rows_shard), dtype=np.float32)
+            h.get_C(c_resident, rows_shard)
+        e2e = run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist if world > 1 else None, total_flops,
+                      c_resident)
     h.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
@@ -506,8 +512,9 @@ def spot_check(h, v, lo, hi, n, precision, Bm, dist, dev, rank):
             "max_rel_err_vs_rounded_operands": worst_r / max(scale, 1e-30)}
 
 
-def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops):
-    """One-shot sparta_vbr_spmm on this rank's shard: host arrays in, host C out."""
+def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_resident=None):
+    """One-shot sparta_vbr_spmm on this rank's shard: host arrays in, host C out.  The C it returns
+    is compared with the resident handle's (which spot_check verified against fp64)."""
     import ctypes as C
     import torch
     import sparta_b200
@@ -555,15 +562,23 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops):
             once()
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
+    diff = 0.0
+    if rows_s and c_resident is not None:
+        scale = float(np.abs(c_resident).max()) or 1.0
+        diff = float(np.abs(a_C[:, :rows_s] - c_resident).max()) / scale
     t_all = torch.tensor([sec, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t_all.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dmax = torch.tensor([diff], dtype=torch.float64, device=dev)
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        diff = float(dmax.item())
         dist.all_reduce(t_all, op=dist.ReduceOp.SUM)
         sec = float(tmax[0].item())
         h2d, d2h = float(t_all[1].item()), float(t_all[2].item())
     return {"value": total_flops * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * sec / steps,
+            "max_rel_diff_vs_resident_handle": diff, "same_result": bool(diff <= 1e-6),
             "call": "sparta_vbr_spmm (host VBR + host B -> host C; upload, repack, kernel, download per call; "
                     "pinned host buffers; wall clock, max over ranks)"}
 
