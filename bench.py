@@ -393,6 +393,11 @@ def run_ours(args, wl):
     # ---- correctness spot check inside the bench (fp64 recomputation of sampled rows)
     check = spot_check(h, v, lo, hi, n, args.precision, Bm, dist if world > 1 else None, dev, rank)
 
+    # ---- optional: assemble the row-partitioned C on every rank with one NCCL all-gather
+    gather = None
+    if args.gather_c and world > 1:
+        gather = gather_c(h, v, cuts, n, rank, world, dev, dist)
+
     # ---- e2e: the one-shot reference-facing call, host buffers in and out (rank-local shard)
     e2e = None
     if not args.no_e2e:
@@ -438,6 +443,7 @@ def run_ours(args, wl):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": check,
+            "gather_c": gather,
             "setup": {"blocking_s": t_block, "vbr_fill_s": t_fill, "matrix_gen_s": t_gen,
                       "a_upload_pack_ms": st["upload_ms"], "b_broadcast_s": t_bcast,
                       "sched_imbalance": st["sched_imbalance"], "grid": st["grid"], "items": st["items"],
@@ -510,6 +516,42 @@ def spot_check(h, v, lo, hi, n, precision, Bm, dist, dev, rank):
     return {"max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol), "block_rows_checked": int(len(pick)),
             "against": "fp64 recomputation of sampled block-rows from the fp32 operands (norm max|dC|/max|C|)",
             "max_rel_err_vs_rounded_operands": worst_r / max(scale, 1e-30)}
+
+
+def gather_c(h, v, cuts, n, rank, world, dev, dist):
+    """C stays row-partitioned by default; this is the optional all-gather (outside the timed
+    region of `value`): the ragged slabs are padded to the tallest, gathered over NCCL and
+    checked -- every rank must end up with every other rank's slab bit for bit."""
+    import torch
+    from sparta_b200 import dist as sd
+    rp = v["row_part"]
+    rows_per_rank = [int(rp[int(cuts[r + 1])] - rp[int(cuts[r])]) for r in range(world)]
+    mine = rows_per_rank[rank]
+    slab = torch.zeros((n, max(mine, 1)), dtype=torch.float32, device=dev)
+    if mine:
+        h.get_C_device(slab.data_ptr(), mine)
+    slab = slab[:, :mine]
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    full = sd.all_gather_C(slab, rows_per_rank, n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # checksum of every slab as its owner computed it vs as this rank received it
+    own = torch.zeros(world, dtype=torch.float64, device=dev)
+    own[rank] = slab.double().sum() if mine else 0.0
+    dist.all_reduce(own)
+    offs = np.concatenate([[0], np.cumsum(rows_per_rank)])
+    got = torch.stack([full[:, offs[r]:offs[r + 1]].double().sum() for r in range(world)])
+    same = bool(torch.equal(own, got)) and bool(torch.equal(full[:, offs[rank]:offs[rank + 1]], slab))
+    ok = torch.tensor([1.0 if same else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"ms": float(t.item()), "bytes_per_rank_out": int(full.numel() * 4), "ok": bool(ok.item() == 1.0),
+            "how": "slabs padded to the tallest, one NCCL all_gather, padding cut away (sparta_b200/dist.py)"}
 
 
 def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_resident=None):
@@ -594,6 +636,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-c", action="store_true", help="multi-GPU: also all-gather C over NCCL and verify it")
     ap.add_argument("--cpu-gflop", type=float, default=16.0, help="size of the cpu_baseline sample")
     ap.add_argument("--cpu-gflop-per-step", type=float, default=8.0,
                     help="--impl reference: nonzero-block GFLOP per thread-step sample")
