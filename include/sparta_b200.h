@@ -250,6 +250,15 @@ int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t blo
                                          const int64_t* nzcount, const int64_t* jab, int64_t n,
                                          const sparta_options* opt, int32_t parts, int64_t* cuts);
 
+/* The modelled partition corrected by MEASURED times: time_scale[block_rows] holds, for every
+ * block-row, measured / modelled kernel time of the shard it belonged to in an earlier partition
+ * (ranks time a few launches, all-gather the times and re-cut). */
+int sparta_partition_block_rows_measured(int64_t rows, int64_t cols, int64_t block_rows,
+                                         int64_t block_col_size, const int64_t* row_part,
+                                         const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                         const sparta_options* opt, int32_t parts,
+                                         const double* time_scale, int64_t* cuts);
+
 /* ---- host-side format builders (no GPU needed; bit-exact with the reference) ---- */
 
 /* Row clustering: BlockingEngine::GetGrouping (src/general/blocking.cpp:633-676) on a flat CSR

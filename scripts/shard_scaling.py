@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--opts", default="", help="extra handle options, e.g. num_ctas=144,l2_slab_mb=160")
     ap.add_argument("--partition", default="area", choices=["area", "model"])
+    ap.add_argument("--feedback", type=int, default=0, help="re-cut this many times with measured / modelled shard times")
     args = ap.parse_args()
     import torch
     wl = bench.WORKLOADS[args.workload]
@@ -40,6 +41,34 @@ def main():
     total_flops = 2.0 * v["nztot"] * n
     extra = {k: int(x) for k, x in (kv.split("=") for kv in args.opts.split(",") if kv)}
     results = []
+    def measure(cuts, world, split):
+        per_rank = []
+        for r in range(world):
+            h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
+                                            v["mab"], precision=args.precision, block_row_begin=int(cuts[r]),
+                                            block_row_end=int(cuts[r + 1]), split_k=split, **extra)
+            h.set_B_device(Bd.data_ptr(), v["cols"], n)
+            st = h.stats()
+            stream = torch.cuda.ExternalStream(h.stream)
+            for _ in range(3):
+                h.run_async()
+            h.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                h.run_async()
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            per_rank.append({"rank": r, "ms": ms, "nz_blocks": st["nz_blocks"], "items": st["items"],
+                             "split_pieces": st["split_pieces"], "zero_tiles": st["zero_tiles"],
+                             "model_imbalance": round(st["sched_imbalance"], 3),
+                             "model_cycles": st["sched_max_cycles"], "chunks": st["chunks"],
+                             "super_rows": st["super_rows"],
+                             "tflops": 2.0 * st["nztot"] * n / ms / 1e9})
+            h.close()
+        return per_rank
+
     for split in [int(x) for x in args.split.split(",")]:
         t1 = None
         for world in [int(x) for x in args.worlds.split(",")]:
@@ -49,40 +78,24 @@ def main():
                                                                  split_k=split, **extra)
             else:
                 cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
-            per_rank = []
-            for r in range(world):
-                h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
-                                                v["mab"], precision=args.precision, block_row_begin=int(cuts[r]),
-                                                block_row_end=int(cuts[r + 1]), split_k=split, **extra)
-                h.set_B_device(Bd.data_ptr(), v["cols"], n)
-                st = h.stats()
-                stream = torch.cuda.ExternalStream(h.stream)
-                for _ in range(3):
-                    h.run_async()
-                h.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(args.steps):
-                    h.run_async()
-                e1.record(stream)
-                e1.synchronize()
-                ms = e0.elapsed_time(e1) / args.steps
-                per_rank.append({"rank": r, "ms": ms, "nz_blocks": st["nz_blocks"], "items": st["items"],
-                                 "split_pieces": st["split_pieces"], "zero_tiles": st["zero_tiles"],
-                                 "model_imbalance": round(st["sched_imbalance"], 3),
-                                 "model_cycles": st["sched_max_cycles"], "chunks": st["chunks"],
-                                 "super_rows": st["super_rows"],
-                                 "tflops": 2.0 * st["nztot"] * n / ms / 1e9})
-                h.close()
-            worst = max(p["ms"] for p in per_rank)
-            if world == 1:
-                t1 = worst
-            rec = {"split_k": split, "world": world, "step_ms": worst, "tflops": total_flops / worst / 1e9,
-                   "efficiency": (t1 / (world * worst)) if t1 else None, "per_rank": per_rank}
-            results.append(rec)
-            print(f"split_k={split} N={world}: step {worst:.3f} ms, {rec['tflops']:.0f} TFLOP/s aggregate, "
-                  f"efficiency {rec['efficiency']:.3f}; per-rank ms " + " ".join(f"{p['ms']:.3f}" for p in per_rank),
-                  flush=True)
+            for attempt in range(args.feedback + 1 if world > 1 else 1):
+                if attempt > 0:   # re-cut with measured / modelled shard times of the previous attempt
+                    cuts = sparta_b200.partition_block_rows_measured(
+                        v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"], n, world, cuts,
+                        [p["ms"] for p in per_rank], [p["model_cycles"] for p in per_rank], precision=args.precision,
+                        split_k=split, **extra)
+                per_rank = measure(cuts, world, split)
+                worst = max(p["ms"] for p in per_rank)
+                if world == 1:
+                    t1 = worst
+                rec = {"split_k": split, "world": world, "feedback_round": attempt, "cuts": [int(c) for c in cuts],
+                       "step_ms": worst, "tflops": total_flops / worst / 1e9,
+                       "efficiency": (t1 / (world * worst)) if t1 else None, "per_rank": per_rank}
+                results.append(rec)
+                print(f"split_k={split} N={world}" + (f" feedback {attempt}" if attempt else "") +
+                      f": step {worst:.3f} ms, {rec['tflops']:.0f} TFLOP/s aggregate, "
+                      f"efficiency {rec['efficiency']:.3f}; per-rank ms " + " ".join(f"{p['ms']:.3f}" for p in per_rank),
+                      flush=True)
     if args.out:
         with open(args.out, "w") as f:
             json.dump(results, f, indent=1)

@@ -1193,10 +1193,39 @@ int sparta_release_workspace(void) {
 // dense head.  Fixed point: start from the area partition; build every shard's schedule; spread
 // its modelled time (the slowest worker's cycles) over its block-rows in proportion to their
 // current weight; re-cut on the new weights; keep the best of a few rounds.
+static int partition_modelled_impl(int64_t rows, int64_t cols, int64_t block_rows,
+                                   int64_t block_col_size, const int64_t* row_part,
+                                   const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                   const sparta_options* opt, int32_t parts, const double* time_scale,
+                                   int64_t* cuts);
+
 int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t block_rows,
                                          int64_t block_col_size, const int64_t* row_part,
                                          const int64_t* nzcount, const int64_t* jab, int64_t n,
                                          const sparta_options* opt, int32_t parts, int64_t* cuts) {
+  return partition_modelled_impl(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, opt, parts,
+                                 nullptr, cuts);
+}
+
+// The same with MEASURED feedback: time_scale[b] = (measured / modelled kernel time) of the shard
+// block-row b belonged to in an earlier partition.  Every shard's modelled time is multiplied by
+// the weight-averaged scale of its block-rows before the cuts are balanced, which removes what
+// the cost model gets systematically wrong about a region of the matrix.
+int sparta_partition_block_rows_measured(int64_t rows, int64_t cols, int64_t block_rows,
+                                         int64_t block_col_size, const int64_t* row_part,
+                                         const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                         const sparta_options* opt, int32_t parts,
+                                         const double* time_scale, int64_t* cuts) {
+  if (!time_scale) return fail(SPARTA_ERR_INVALID, "time_scale is NULL");
+  return partition_modelled_impl(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, opt, parts,
+                                 time_scale, cuts);
+}
+
+static int partition_modelled_impl(int64_t rows, int64_t cols, int64_t block_rows,
+                                   int64_t block_col_size, const int64_t* row_part,
+                                   const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                   const sparta_options* opt, int32_t parts, const double* time_scale,
+                                   int64_t* cuts) {
   if (block_rows < 0 || parts <= 0 || !cuts || cols <= 0 || block_col_size <= 0 || n <= 0 ||
       (block_rows && (!row_part || !nzcount)))
     return fail(SPARTA_ERR_INVALID, "invalid partition request");
@@ -1247,6 +1276,11 @@ int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t blo
       if (!*e) e = build_assignment(st, so, n, cols, &as);
       if (*e) return fail(SPARTA_ERR_INVALID, e);
       t[i] = as.max_cta_cost;
+      if (time_scale) {
+        double ws = 0, w = 0;
+        for (int64_t b = cur[i]; b < cur[i + 1]; ++b) { ws += weight[b] * time_scale[b]; w += weight[b]; }
+        if (w > 0) t[i] *= ws / w;
+      }
       worst = std::max(worst, t[i]);
     }
     if (best_worst < 0 || worst < best_worst) { best_worst = worst; best = cur; }

@@ -93,6 +93,8 @@ SIGNATURES = {
     "sparta_partition_block_rows": (C.c_int, [C.c_int64, _vp, _vp, C.c_int32, _vp]),
     "sparta_partition_block_rows_modelled": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp,
                                                        C.c_int64, C.POINTER(Options), C.c_int32, _vp]),
+    "sparta_partition_block_rows_measured": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp,
+                                                       C.c_int64, C.POINTER(Options), C.c_int32, _vp, _vp]),
     "sparta_host_blocking": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
                                        C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp]),
@@ -183,6 +185,25 @@ def partition_block_rows_modelled(rows, cols, block_col_size, row_part, nzcount,
     o = make_options(**opts)
     _check(load().sparta_partition_block_rows_modelled(rows, cols, len(nzcount), block_col_size, _ptr(row_part),
                                                        _ptr(nzcount), _ptr(jab), n, C.byref(o), parts, _ptr(cuts)))
+    return cuts
+
+
+def partition_block_rows_measured(rows, cols, block_col_size, row_part, nzcount, jab, n, parts, prev_cuts,
+                                  measured_ms, modelled_cycles, **opts):
+    """The modelled partition corrected by measured shard times of an earlier partition `prev_cuts`:
+    every block-row gets the measured / modelled ratio of the shard it was in (ratios are
+    normalised to mean 1, so the clock rate does not matter)."""
+    row_part, nzcount, jab = _i64(row_part), _i64(nzcount), _i64(jab)
+    ratio = np.asarray(measured_ms, dtype=np.float64) / np.maximum(np.asarray(modelled_cycles, dtype=np.float64), 1.0)
+    ratio = ratio / ratio.mean()
+    scale = np.ones(len(nzcount), dtype=np.float64)
+    for r in range(len(prev_cuts) - 1):
+        scale[int(prev_cuts[r]):int(prev_cuts[r + 1])] = ratio[r]
+    cuts = np.zeros(parts + 1, dtype=np.int64)
+    o = make_options(**opts)
+    _check(load().sparta_partition_block_rows_measured(rows, cols, len(nzcount), block_col_size, _ptr(row_part),
+                                                       _ptr(nzcount), _ptr(jab), n, C.byref(o), parts,
+                                                       scale.ctypes.data_as(C.c_void_p), _ptr(cuts)))
     return cuts
 
 

@@ -285,3 +285,28 @@ def test_leftover_workers_form_a_narrow_team(oracle, lib, n, num_ctas, expect):
     assert max(load) <= 1.35 * np.mean(load)                         # ... and is not the straggler
     Cm = sched_interp.run_plan(plan, v["mab"], Bm, 1024, n, v["rows"])
     assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
+
+
+def test_measured_partition_moves_cuts_towards_slow_shards(lib):
+    """sparta_partition_block_rows_measured: equal measured / modelled ratios reproduce the modelled
+    cuts; a shard that ran slower than modelled gives block-rows away."""
+    rng = np.random.default_rng(72)
+    row_part = np.arange(0, 64 * 201, 64)
+    nzcount, jab = [], []
+    for b in range(200):
+        cols = np.flatnonzero(rng.random(256) < 0.3)
+        nzcount.append(len(cols)); jab.extend(cols.tolist())
+    nzcount, jab = np.array(nzcount), np.array(jab)
+    rows, n = int(row_part[-1]), 1024
+    base = sparta_b200.partition_block_rows_modelled(rows, 256 * 64, 64, row_part, nzcount, jab, n, 4)
+    model = []
+    for i in range(4):
+        p = sparta_b200.vbr_plan(rows, 256 * 64, 64, row_part, nzcount, jab, n, block_row_begin=int(base[i]),
+                                 block_row_end=int(base[i + 1]))
+        model.append(p["stats"]["sched_max_cycles"])
+    same = sparta_b200.partition_block_rows_measured(rows, 256 * 64, 64, row_part, nzcount, jab, n, 4, base,
+                                                     [m * 1e-6 for m in model], model)
+    assert np.array_equal(same, base)
+    slow_first = sparta_b200.partition_block_rows_measured(rows, 256 * 64, 64, row_part, nzcount, jab, n, 4, base,
+                                                           [model[0] * 1.3e-6] + [m * 1e-6 for m in model[1:]], model)
+    assert slow_first[1] < base[1] and slow_first[0] == 0 and slow_first[-1] == 200
