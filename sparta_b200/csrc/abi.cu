@@ -471,8 +471,11 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
       // tail (~64 GB/s on the 16-core bench host), split so that both finish together.
       int64_t head = 0;
       cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost)
-        head = src_elems * 2 / 5 / 64 * 64;
+      if (cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        int pct = 50;   // share of the array the copy engine takes; SPARTA_UPLOAD_HEAD_PCT overrides (0..100)
+        if (const char* e = getenv("SPARTA_UPLOAD_HEAD_PCT")) pct = std::max(0, std::min(100, atoi(e)));
+        head = src_elems * pct / 100 / 64 * 64;
+      }
       else
         cudaGetLastError();
       const int64_t tail = src_elems - head;
