@@ -75,22 +75,18 @@ def make_matrix(wl):
 
 def make_grouping(wl, N, rowptr, colind):
     """Row clustering through the product's host layer (bit-exact with the reference's
-    BlockingEngine::GetGrouping, src/general/blocking.cpp:633)."""
+    BlockingEngine::GetGrouping, src/general/blocking.cpp:633), behind the LIBRARY's grouping cache
+    (sparta_host_blocking_cached: the reference's `.g` file format keyed on the CSR pattern and the
+    flags, include/sparta_b200.h).  cache/ in the repo holds the groupings of the bench workloads so
+    that GPU minutes are not spent on CPU blocking (-a 4 at 2^18 rows: 17 minutes)."""
     from sparta_b200 import lib
     if wl["algo"] == 2:
         return np.arange(N, dtype=np.int64) // wl["rb"]
-    cache = os.environ.get("SPARTA_BENCH_CACHE")   # like the reference's .g grouping files (Matrix_Blocking.cpp:24-32)
-    key = None
-    if cache:
-        os.makedirs(cache, exist_ok=True)
-        key = os.path.join(cache, f"grouping_{wl['kind']}{wl['scale']}_{wl['density']}_a{wl['algo']}_b{wl['w']}_B{wl['rb']}_t{wl['tau']}.npy")
-        if os.path.exists(key):
-            return np.load(key)
-    g = lib.host_blocking(N, N, rowptr, colind, algo=wl["algo"], tau=wl["tau"],
-                             block_col_size=wl["w"], row_block_size=wl["rb"], sim_measure=1,
-                             use_pattern=True, use_group=False)
-    if key:
-        np.save(key, g)
+    cache = os.environ.get("SPARTA_BENCH_CACHE", os.path.join(ROOT, "cache"))
+    g, hit = lib.host_blocking_cached(cache, N, N, rowptr, colind, algo=wl["algo"], tau=wl["tau"],
+                                      block_col_size=wl["w"], row_block_size=wl["rb"], sim_measure=1,
+                                      use_pattern=True, use_group=False)
+    log(f"[bench] grouping: {'cache hit' if hit else 'computed and cached'} ({cache})")
     return g
 
 
@@ -457,7 +453,7 @@ def run_ours(args, wl):
 
 def tuning_opts(args):
     o = {}
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline"):
         val = getattr(args, k)
         if val:
             o[k] = val
@@ -643,7 +639,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--partition", default="model", choices=["model", "area"],
                     help="multi-GPU block-row partition: balanced on modelled shard time (default) or on nonzero-block area")
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline"):
         ap.add_argument("--" + k.replace("_", "-"), dest=k, type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

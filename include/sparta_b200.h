@@ -56,7 +56,9 @@ typedef struct sparta_options {
   int32_t panel_stages;  /* smem pipeline depth, 2..8 (default 5) */
   int32_t num_ctas;      /* persistent grid size (default: SM count) */
   int64_t block_row_begin; /* shard: first block-row (default 0) */
-  int64_t block_row_end;   /* shard: one past the last block-row (default: all) */
+  int64_t block_row_end;   /* shard: one past the last block-row.  With explicit_range = 0 a value <= 0 means
+                              "to the end" (so a zeroed struct selects everything); set explicit_range = 1 to
+                              have [begin, end) taken literally, including an EMPTY shard (begin == end) */
   int32_t cta_pair;      /* 0/2: CTA pairs, tcgen05 cta_group::2, 256-column tiles (default); 1: single CTAs */
   int32_t row_order;     /* 0/2: super-rows group block-rows of similar block count (default); 1: input order */
   int32_t l2_slab_mb;    /* B columns walked per pass over A, in MiB of B (default 160) */
@@ -70,7 +72,15 @@ typedef struct sparta_options {
   int32_t fuse_rows;     /* runs of consecutive block-rows whose heights add up to <= 16 share one 16-row MMA
                             segment with the union of their column-block lists (variable-height blockings
                             produce thousands of block-rows one or two rows tall).  0: on (default), 1: off */
-  int32_t reserved[2];
+  int32_t explicit_range; /* 1: block_row_begin / block_row_end are literal (an empty range is an empty shard) */
+  int32_t pipeline;      /* shared-memory pipeline of the SpMM kernel.  0: fixed slots when at least 3 stages of
+                            (B panel + the handle's largest chunk of A images) fit, else the byte ring (default);
+                            1: byte ring (A images of the stages in flight share one ring; one copy warp);
+                            2: fixed slots */
+  int32_t copy_warps;    /* fixed slots only: warps per CTA that issue the TMA / bulk copies, taking alternate
+                            chunks.  0/2: two (default; one thread cannot start more than one pipeline stage per
+                            ~600 cycles, profiles/r2_copy_issue_microbench.txt), 1: one */
+  int32_t reserved2[3];
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */
@@ -279,6 +289,26 @@ int sparta_host_blocking(int64_t rows, int64_t cols, const int64_t* rowptr, cons
                          int32_t sim_measure, int32_t use_pattern, int32_t use_groups,
                          int32_t force_fixed_size, int32_t flags, int64_t* grouping,
                          sparta_blocking_stats* stats);
+
+/* Grouping files.  The reference persists a grouping as `<outfile>.g`, one group id per line
+ * (test/general/Matrix_Blocking.cpp:24-32, src/general/utilities.cpp:240-243) and reloads such a file
+ * in test/general/Matrix_Analysis.cpp:10-32.  sparta_grouping_save / _load read and write exactly that
+ * format, plus a sidecar `<path>.key` (hex key, row count, flags as text): _load with key != 0 fails
+ * unless the sidecar holds the same key.  sparta_blocking_key hashes the CSR pattern and the blocking
+ * flags (0 on invalid input).  sparta_host_blocking_cached looks `<cache_dir>/grouping_<key>.g` up,
+ * runs sparta_host_blocking and stores the result on a miss; *hit (may be NULL) tells which happened.
+ * Blocking a 2^18-row R-MAT with -a 4 takes 17 minutes of CPU; the file is 1.6 MB. */
+int sparta_grouping_save(const char* path, int64_t rows, const int64_t* grouping, uint64_t key);
+int sparta_grouping_load(const char* path, int64_t rows, int64_t* grouping, uint64_t key);
+uint64_t sparta_blocking_key(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
+                             int32_t algo, float tau, int64_t block_col_size, int64_t row_block_size,
+                             int32_t sim_measure, int32_t use_pattern, int32_t use_groups,
+                             int32_t force_fixed_size);
+int sparta_host_blocking_cached(const char* cache_dir, int64_t rows, int64_t cols, const int64_t* rowptr,
+                                const int64_t* colind, int32_t algo, float tau, int64_t block_col_size,
+                                int64_t row_block_size, int32_t sim_measure, int32_t use_pattern,
+                                int32_t use_groups, int32_t force_fixed_size, int32_t flags,
+                                int64_t* grouping, sparta_blocking_stats* stats, int32_t* hit);
 
 /* get_permutation / get_partition (src/general/utilities.cpp:8-43).  perm[n]; part needs
  * n+1 slots, *part_len receives block_rows+1. */

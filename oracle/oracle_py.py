@@ -164,6 +164,22 @@ class Oracle:
                                         _p(mab), _p(Bt), m, m, _p(Cm), m)
         return Cm.reshape(cols, m)
 
+    def ref_multiplyBA_literal(self, v, Bt, m):
+        """cublas_blockmat_multiplyBA (cuda_utilities.cpp:640-690) index for index, GEMMs done in
+        fp32 on the CPU.  Bt: [rows, m] (row k = column k of the m x rows column-major B).
+        Returns (C as [cols_padded, m], out_of_range flag)."""
+        w = int(v["block_col_size"])
+        cols_pad = ((int(v["cols"]) - 1) // w + 1) * w
+        Bt = _f(Bt).reshape(-1)
+        Cm = np.zeros(m * cols_pad, dtype=np.float32)
+        rp, nz, jab, mab = _l(v["row_part"]), _l(v["nzcount"]), _l(v["jab"]), _f(v["mab"])
+        self.lib.oracle_ref_multiplyBA_literal.restype = C.c_int
+        self.lib.oracle_ref_multiplyBA_literal.argtypes = [C.c_long, C.c_long] + [C.c_void_p] * 5 + \
+            [C.c_long, C.c_long, C.c_void_p]
+        oor = self.lib.oracle_ref_multiplyBA_literal(len(nz), w, _p(rp), _p(nz), _p(jab), _p(mab), _p(Bt),
+                                                     len(Bt), m, _p(Cm))
+        return Cm.reshape(cols_pad, m), bool(oor)
+
     def csr_multiply(self, rows, rowptr, colind, val, pattern_only, Bm, n):
         rowptr, colind, val, Bm = _l(rowptr), _l(colind), _f(val), _f(Bm).reshape(-1)
         Cm = np.zeros(n * rows, dtype=np.float32)

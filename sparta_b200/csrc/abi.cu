@@ -97,6 +97,8 @@ struct sparta_handle {
   ScheduleOptions sopt;
   int b_row_major = 0, c_row_major = 0, accumulate = 0;
   int panel_stages = 4, a_ring_bytes = 0;
+  int a_slot_bytes = 0;   // > 0: fixed-slot pipeline (spmm_kernel.h)
+  int producers = 1;
   int64_t cols = 0, block_rows = 0, w = 0;
   int64_t rows = 0;   // C rows of the shard
   Structure st;   // jobs are dropped after packing
@@ -139,9 +141,55 @@ static void resolve_options(const sparta_options* in, sparta_options* o) {
   if (o->panel_stages == 0) o->panel_stages = 5;
 }
 
+// One past the last unit of the shard.  A zeroed options struct selects everything; with
+// explicit_range the pair [begin, end) is literal, so begin == end is an EMPTY shard (a balanced
+// partition may hand a rank nothing) instead of silently meaning "all".
+static int64_t range_end(const sparta_options& o, int64_t total) {
+  if (o.explicit_range) return o.block_row_end;
+  return o.block_row_end > 0 ? o.block_row_end : total;
+}
+
+// Persistent grid size of the host-only planning entry points (plans, modelled partitions): the
+// SM count of the current device when there is one, else the B200's 148.
+static int default_grid_ctas() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    cached = sms;
+  else {
+    cudaGetLastError();
+    cached = 148;
+  }
+  return cached;
+}
+
 static int ring_bytes_for(int panel_stages) {
   int b = kSmemMax - 1024 - kSmemCtrlBytes - panel_stages * kPanelBytes;
   return b / 1024 * 1024;
+}
+
+// Shared-memory pipeline of a handle (spmm_kernel.h): fixed slots -- every stage owns room for the
+// largest chunk's A images -- when at least 3 such stages fit (they do unless a single-CTA handle
+// has 512-row chunks), else the byte ring.  Slots make the producer's per-chunk work short enough
+// for two copy warps to matter; chunks of 1-2 members (ER-like matrices, variable-height blockings)
+// are bound by how fast stages can be STARTED, not by bytes.
+static void pick_pipeline(uint32_t max_chunk_bytes, const sparta_options& o, int* stages, int* ring_bytes,
+                          int* slot_bytes, int* producers) {
+  const int avail = kSmemMax - 1024 - kSmemCtrlBytes;
+  const int slot = static_cast<int>((std::max<uint32_t>(max_chunk_bytes, 1024) + 1023) / 1024 * 1024);
+  const int fit = std::min(kMaxPanelStages, avail / (kPanelBytes + slot));
+  const bool slots = o.pipeline == 2 ? fit >= 2 : (o.pipeline == 1 ? false : fit >= 3);
+  if (slots) {
+    *stages = fit;
+    *slot_bytes = slot;
+    *ring_bytes = fit * slot;
+    *producers = o.copy_warps == 1 ? 1 : 2;
+  } else {
+    *slot_bytes = 0;
+    *producers = 1;   // stages and ring as set from the options
+  }
 }
 
 // ---- BlockRows builders (format adapters) ---------------------------------
@@ -413,14 +461,28 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   h->sopt.precision = o.precision;
   h->sopt.seg_rows = o.seg_rows;
   h->sopt.acc_cols = o.acc_cols;
-  h->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : sms;
   h->sopt.pair = o.cta_pair != 1;
+  h->panel_stages = o.panel_stages;
+  h->a_ring_bytes = ring_bytes_for(o.panel_stages);
+  {
+    // The persistent grid must be co-resident (split plans synchronise the grid inside the
+    // kernel): never launch more CTAs than the device holds at once at this footprint.
+    int cap = 0;
+    const cudaError_t ce = spmm_max_coresident_ctas(h->sopt.pair, o.precision == SPARTA_TF32, 0,
+                                                    spmm_smem_bytes(h->panel_stages, h->a_ring_bytes), &cap);
+    if (ce != cudaSuccess) { free_handle(h); return fail_cuda(ce, "cudaOccupancyMaxActiveClusters"); }
+    if (cap <= 0) { free_handle(h); return fail(SPARTA_ERR_CUDA, "the device cannot hold a single CTA of the SpMM kernel"); }
+    if (o.num_ctas > cap) {
+      free_handle(h);
+      return fail(SPARTA_ERR_INVALID, "num_ctas exceeds the CTAs the device can hold at the same time (" +
+                                          std::to_string(cap) + "); the persistent grid must be co-resident");
+    }
+    h->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : std::min(sms, cap);
+  }
   h->sopt.sort_rows = o.row_order != 1;
   h->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
   h->sopt.max_chain = o.max_chain;
   h->sopt.split = o.split_k;
-  h->panel_stages = o.panel_stages;
-  h->a_ring_bytes = ring_bytes_for(o.panel_stages);
   h->accumulate = o.accumulate ? 1 : 0;
   h->b_row_major = o.b_layout == SPARTA_LAYOUT_DEFAULT ? default_row_major : (o.b_layout == SPARTA_ROW_MAJOR);
   h->c_row_major = o.c_layout == SPARTA_LAYOUT_DEFAULT ? default_row_major : (o.c_layout == SPARTA_ROW_MAJOR);
@@ -524,6 +586,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
                 : "a chunk's A images exceed the shared-memory ring; lower acc_cols or panel_stages");
   }
   h->rows = h->st.rows;
+  pick_pipeline(h->st.max_chunk_bytes, o, &h->panel_stages, &h->a_ring_bytes, &h->a_slot_bytes, &h->producers);
   H_TRY(upload_vec(h->st.segs, &h->d_segs, h->stream));
   H_TRY(upload_vec(h->st.srows, &h->d_srows, h->stream));
   H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
@@ -582,7 +645,7 @@ static int vbr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int6
   sparta_options o;
   resolve_options(opt, &o);
   const int64_t lo = o.block_row_begin;
-  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : block_rows;
+  const int64_t hi = range_end(o, block_rows);
   BlockRows br;
   int64_t src_lo = 0, src_hi = 0;
   const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, lo, hi, &br, &src_lo, &src_hi);
@@ -614,7 +677,7 @@ static int vbr_create_ba_impl(sparta_handle** out, int64_t rows, int64_t cols, i
   resolve_options(opt, &o);
   const int64_t bc = (cols - 1) / block_col_size + 1;
   const int64_t lo = o.block_row_begin;
-  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : bc;
+  const int64_t hi = range_end(o, bc);
   BlockRows br;
   int64_t src_hi = 0;
   const char* e = blockrows_from_vbr_transposed(cols, block_rows, block_col_size, row_part, nzcount, jab, lo, hi,
@@ -654,7 +717,7 @@ static int bellpack_create_impl(sparta_handle** out, int64_t rows, int64_t cols,
   sparta_options o;
   resolve_options(opt, &o);
   const int64_t lo = o.block_row_begin;
-  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : ellColInd_rows;
+  const int64_t hi = range_end(o, ellColInd_rows);
   BlockRows br;
   int64_t src_lo = 0, src_hi = 0;
   const char* e = blockrows_from_bell(ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd, lo, hi, &br, &src_lo, &src_hi);
@@ -686,7 +749,7 @@ static int csr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, cons
   sparta_options o;
   resolve_options(opt, &o);
   const int64_t lo = o.block_row_begin;
-  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : rows;
+  const int64_t hi = range_end(o, rows);
   if (lo < 0 || hi > rows || lo > hi) return fail(SPARTA_ERR_INVALID, "row range out of bounds");
   for (int64_t i = lo; i < hi; ++i)
     if (rowptr[i + 1] < rowptr[i]) return fail(SPARTA_ERR_INVALID, "rowptr must be non-decreasing");
@@ -944,6 +1007,8 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   p.n = static_cast<int32_t>(h->n);
   p.accumulate = h->accumulate;
   p.pair = h->st.pair;
+  p.producers = h->producers;
+  p.a_slot_bytes = h->a_slot_bytes;
   p.trace = trace;
   p.trace_worker = trace_worker;
   p.trace_cap = trace_cap;
@@ -957,7 +1022,13 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   const char* err = "";
   if (!h->as.zero_jobs.empty() && !h->accumulate) {
     // split pieces add partial sums: their C tiles start from zero (C := A*B semantics); the
-    // kernel zeroes them itself and every CTA of the grid reports in on the counter
+    // kernel zeroes them itself and every CTA of the grid reports in on the counter.  The counter
+    // target is a per-launch kernel parameter, so a captured launch must not be replayed.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU_TRY(cudaStreamIsCapturing(h->stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(SPARTA_ERR_STATE, "a handle whose plan has split pieces cannot be captured into a CUDA graph; "
+                                    "create it with split_k = 1");
     if (!h->d_sync) {
       CU_TRY(dev_alloc(&h->d_sync, sizeof(unsigned long long), h->stream));
       CU_TRY(cudaMemsetAsync(h->d_sync, 0, sizeof(unsigned long long), h->stream));
@@ -1239,7 +1310,7 @@ static int partition_modelled_impl(int64_t rows, int64_t cols, int64_t block_row
   so.precision = o.precision;
   so.seg_rows = o.seg_rows;
   so.acc_cols = o.acc_cols;
-  so.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  so.num_ctas = o.num_ctas > 0 ? o.num_ctas : default_grid_ctas();
   so.pair = o.cta_pair != 1;
   so.sort_rows = o.row_order != 1;
   so.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
@@ -1332,6 +1403,69 @@ int sparta_host_blocking(int64_t rows, int64_t cols, const int64_t* rowptr, cons
   return SPARTA_OK;
 }
 
+int sparta_grouping_save(const char* path, int64_t rows, const int64_t* grouping, uint64_t key) {
+  if (!path || rows < 0 || (rows && !grouping)) return fail(SPARTA_ERR_INVALID, "NULL path or grouping");
+  const char* e = grouping_save(path, rows, grouping, key, "");
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  return SPARTA_OK;
+}
+
+int sparta_grouping_load(const char* path, int64_t rows, int64_t* grouping, uint64_t key) {
+  if (!path || rows < 0 || (rows && !grouping)) return fail(SPARTA_ERR_INVALID, "NULL path or grouping");
+  const char* e = grouping_load(path, rows, grouping, key);
+  if (*e) return fail(SPARTA_ERR_INVALID, std::string(e) == "miss" ? "no grouping file with this key" : e);
+  return SPARTA_OK;
+}
+
+uint64_t sparta_blocking_key(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
+                             int32_t algo, float tau, int64_t block_col_size, int64_t row_block_size,
+                             int32_t sim_measure, int32_t use_pattern, int32_t use_groups,
+                             int32_t force_fixed_size) {
+  if (rows < 0 || !rowptr || (rows && rowptr[rows] && !colind)) return 0;
+  return blocking_key(rows, cols, rowptr, colind, algo, tau, block_col_size, row_block_size, sim_measure,
+                      use_pattern, use_groups, force_fixed_size);
+}
+
+int sparta_host_blocking_cached(const char* cache_dir, int64_t rows, int64_t cols, const int64_t* rowptr,
+                                const int64_t* colind, int32_t algo, float tau, int64_t block_col_size,
+                                int64_t row_block_size, int32_t sim_measure, int32_t use_pattern,
+                                int32_t use_groups, int32_t force_fixed_size, int32_t flags,
+                                int64_t* grouping, sparta_blocking_stats* stats, int32_t* hit) {
+  if (hit) *hit = 0;
+  if (!cache_dir || !*cache_dir)
+    return sparta_host_blocking(rows, cols, rowptr, colind, algo, tau, block_col_size, row_block_size, sim_measure,
+                                use_pattern, use_groups, force_fixed_size, flags, grouping, stats);
+  if (rows < 0 || !rowptr || (rows && !grouping) || (rows && rowptr[rows] && !colind))
+    return fail(SPARTA_ERR_INVALID, "NULL CSR or grouping array");
+  const auto t0 = std::chrono::steady_clock::now();
+  const uint64_t key = blocking_key(rows, cols, rowptr, colind, algo, tau, block_col_size, row_block_size,
+                                    sim_measure, use_pattern, use_groups, force_fixed_size);
+  char name[96];
+  snprintf(name, sizeof(name), "/grouping_%016llx.g", static_cast<unsigned long long>(key));
+  const std::string path = std::string(cache_dir) + name;
+  const char* e = grouping_load(path.c_str(), rows, grouping, key);
+  if (!*e) {
+    if (hit) *hit = 1;
+    if (stats) {   // the merge statistics are not stored: a hit reports the lookup time only
+      memset(stats, 0, sizeof(*stats));
+      stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return SPARTA_OK;
+  }
+  if (std::string(e) != "miss") return fail(SPARTA_ERR_INVALID, e);
+  const int rc = sparta_host_blocking(rows, cols, rowptr, colind, algo, tau, block_col_size, row_block_size,
+                                      sim_measure, use_pattern, use_groups, force_fixed_size, flags, grouping, stats);
+  if (rc) return rc;
+  char note[256];
+  snprintf(note, sizeof(note), "rows %lld cols %lld nnz %lld -a %d -t %g -b %lld -B %lld -m %d -p %d -g %d -F %d",
+           static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(rowptr[rows]), algo,
+           static_cast<double>(tau), static_cast<long long>(block_col_size), static_cast<long long>(row_block_size),
+           sim_measure, use_pattern, use_groups, force_fixed_size);
+  e = grouping_save(path.c_str(), rows, grouping, key, note);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);   // an unwritable cache directory is the caller's mistake
+  return SPARTA_OK;
+}
+
 int sparta_host_permutation(int64_t n, const int64_t* grouping, int64_t* perm) {
   if (n < 0 || (n && (!grouping || !perm))) return fail(SPARTA_ERR_INVALID, "NULL grouping or perm");
   host_permutation(grouping, n, perm);
@@ -1414,14 +1548,14 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
   BlockRows br;
   int64_t src_lo = 0, src_hi = 0;
   const int64_t lo = o.block_row_begin;
-  const int64_t hi = o.block_row_end > 0 ? o.block_row_end : block_rows;
+  const int64_t hi = range_end(o, block_rows);
   const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, lo, hi, &br, &src_lo, &src_hi);
   if (*e) return fail(SPARTA_ERR_INVALID, e);
   sparta_plan* p = new sparta_plan();
   p->sopt.precision = o.precision;
   p->sopt.seg_rows = o.seg_rows;
   p->sopt.acc_cols = o.acc_cols;
-  p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : default_grid_ctas();
   p->sopt.pair = o.cta_pair != 1;
   p->sopt.sort_rows = o.row_order != 1;
   p->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
@@ -1455,14 +1589,14 @@ int sparta_vbr_plan_create_BA(sparta_plan** out, int64_t rows, int64_t cols, int
   BlockRows br;
   int64_t src_hi = 0;
   const char* e = blockrows_from_vbr_transposed(cols, block_rows, block_col_size, row_part, nzcount, jab,
-                                                o.block_row_begin, o.block_row_end > 0 ? o.block_row_end : bc,
+                                                o.block_row_begin, range_end(o, bc),
                                                 &br, &src_hi);
   if (*e) return fail(SPARTA_ERR_INVALID, e);
   sparta_plan* p = new sparta_plan();
   p->sopt.precision = o.precision;
   p->sopt.seg_rows = o.seg_rows;
   p->sopt.acc_cols = o.acc_cols;
-  p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : 148;
+  p->sopt.num_ctas = o.num_ctas > 0 ? o.num_ctas : default_grid_ctas();
   p->sopt.pair = o.cta_pair != 1;
   p->sopt.sort_rows = o.row_order != 1;
   p->sopt.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;

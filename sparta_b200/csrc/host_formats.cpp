@@ -6,8 +6,13 @@
 //   prepare_cusparse_BLOCKEDELLPACK   src/cuda/cuda_utilities.cpp:1656-1710
 #include "host_formats.h"
 
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 #include <numeric>
+#include <string>
 #include <thread>
 
 namespace sparta {
@@ -148,6 +153,75 @@ const char* host_bellpack_from_vbr(int64_t rows, int64_t cols, int64_t bs, const
       }
     }
   });
+  return "";
+}
+
+// ---- grouping cache (see host_formats.h) ---------------------------------------------------------
+
+static inline uint64_t fnv_mix(uint64_t h, const void* data, size_t bytes) {
+  // FNV-1a over 8-byte words (the arrays are int64); the tail bytes one by one
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  size_t i = 0;
+  for (; i + 8 <= bytes; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x100000001B3ull;
+  }
+  for (; i < bytes; ++i) h = (h ^ p[i]) * 0x100000001B3ull;
+  return h;
+}
+
+uint64_t blocking_key(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind, int32_t algo,
+                      float tau, int64_t block_col_size, int64_t row_block_size, int32_t sim_measure,
+                      int32_t use_pattern, int32_t use_groups, int32_t force_fixed_size) {
+  uint64_t h = 0xCBF29CE484222325ull;
+  const int64_t head[9] = {rows, cols, algo, block_col_size, row_block_size, sim_measure, use_pattern != 0,
+                           use_groups != 0, force_fixed_size != 0};
+  h = fnv_mix(h, head, sizeof(head));
+  h = fnv_mix(h, &tau, sizeof(tau));
+  h = fnv_mix(h, rowptr, static_cast<size_t>(rows + 1) * sizeof(int64_t));
+  h = fnv_mix(h, colind, static_cast<size_t>(rowptr[rows]) * sizeof(int64_t));
+  return h ? h : 1;   // 0 means "unchecked"
+}
+
+const char* grouping_save(const char* path, int64_t rows, const int64_t* grouping, uint64_t key, const char* note) {
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "w");
+  if (!f) return "cannot create the grouping file";
+  for (int64_t i = 0; i < rows; ++i) fprintf(f, "%lld\n", static_cast<long long>(grouping[i]));
+  if (fclose(f) != 0) return "write error on the grouping file";
+  if (rename(tmp.c_str(), path) != 0) return "cannot move the grouping file into place";
+  FILE* k = fopen((std::string(path) + ".key").c_str(), "w");
+  if (!k) return "cannot create the grouping key file";
+  fprintf(k, "%016llx %lld\n%s\n", static_cast<unsigned long long>(key), static_cast<long long>(rows), note ? note : "");
+  fclose(k);
+  return "";
+}
+
+const char* grouping_load(const char* path, int64_t rows, int64_t* grouping, uint64_t key) {
+  if (key) {
+    FILE* k = fopen((std::string(path) + ".key").c_str(), "r");
+    if (!k) return "miss";
+    unsigned long long have = 0;
+    long long have_rows = -1;
+    const int got = fscanf(k, "%llx %lld", &have, &have_rows);
+    fclose(k);
+    if (got != 2 || have != key || have_rows != rows) return "miss";
+  }
+  FILE* f = fopen(path, "r");
+  if (!f) return "miss";
+  // one integer per line, like read_grouping_file (Matrix_Analysis.cpp:10-32)
+  char line[64];
+  int64_t i = 0;
+  while (i < rows && fgets(line, sizeof(line), f)) {
+    char* end = nullptr;
+    const long long v = strtoll(line, &end, 10);
+    if (end == line) { fclose(f); return "the grouping file holds a line that is not a number"; }
+    grouping[i++] = v;
+  }
+  const bool more = fgets(line, sizeof(line), f) != nullptr && line[0] != '\n' && line[0] != 0;
+  fclose(f);
+  if (i != rows || more) return "the grouping file does not have one entry per row";
   return "";
 }
 

@@ -27,4 +27,17 @@ const char* host_vbr_fill(int64_t rows, int64_t cols, const int64_t* rowptr, con
 const char* host_bellpack_from_vbr(int64_t rows, int64_t cols, int64_t bs, const int64_t* nzcount,
                                    const int64_t* jab, const float* mab, int threads, HostBell* out);
 
+// ---- grouping cache -----------------------------------------------------------------------------
+// The reference can persist a grouping as `<outfile>.g`, one group id per line
+// (test/general/Matrix_Blocking.cpp:24-32, src/general/utilities.cpp:240-243), and reload it
+// (test/general/Matrix_Analysis.cpp:10-32).  The cache keeps exactly that file format, so either
+// side can read the other's files, and adds a sidecar `<file>.key` holding a 64-bit key of the
+// CSR pattern and the blocking flags, so a stale file is never served for a different input.
+uint64_t blocking_key(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind, int32_t algo,
+                      float tau, int64_t block_col_size, int64_t row_block_size, int32_t sim_measure,
+                      int32_t use_pattern, int32_t use_groups, int32_t force_fixed_size);
+const char* grouping_save(const char* path, int64_t rows, const int64_t* grouping, uint64_t key, const char* note);
+// key == 0: do not check the sidecar.  Returns "" on success; "miss" when the file or its key is absent / different.
+const char* grouping_load(const char* path, int64_t rows, int64_t* grouping, uint64_t key);
+
 }  // namespace sparta

@@ -204,11 +204,23 @@ __global__ void scatter_values_kernel(const int64_t* __restrict__ idx, const flo
     dst[idx[i]] = val[i];
 }
 
+// grid cap of the grid-stride helper kernels: 16 CTAs per SM of the current device
+static int64_t stride_grid_cap() {
+  static int64_t cached = 0;
+  if (cached) return cached;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    sms = 148;
+  cached = static_cast<int64_t>(sms) * 16;
+  return cached;
+}
+
 cudaError_t scatter_values(const int64_t* idx_dev, const float* val_dev, int64_t nnz, float* dst_dev,
                            cudaStream_t stream) {
   if (nnz <= 0) return cudaSuccess;
   int64_t grid = (nnz + 255) / 256;
-  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid > stride_grid_cap()) grid = stride_grid_cap();
   scatter_values_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(idx_dev, val_dev, nnz, dst_dev);
   return cudaGetLastError();
 }
@@ -235,7 +247,7 @@ cudaError_t permute_rows(const float* src, int64_t src_sr, int64_t src_sj, float
   if (rows == 0 || n == 0) return cudaSuccess;
   const int64_t total = rows * n;
   int64_t grid = (total + 255) / 256;
-  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid > stride_grid_cap()) grid = stride_grid_cap();
   permute_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(src, src_sr, src_sj, dst, dst_sr, dst_sj,
                                                                      row_map_dev, rows, n);
   return cudaGetLastError();

@@ -14,6 +14,9 @@
 //   warp 0   : TMA producer.  Per chunk: one 2-D tensor load of the B row-panel
 //              (128 columns x 128 bytes of k, SWIZZLE_128B) and one bulk copy of
 //              the chunk's packed A images (already in MMA smem byte order).
+//   warp 6   : second TMA producer (kSlots variant): the two warps take alternate
+//              chunks, because ONE thread cannot start more than one pipeline stage
+//              per ~600 cycles whatever its size (profiles/r2_copy_issue_microbench.txt).
 //   warp 1   : single-thread tcgen05.mma issuer; accumulators live in TMEM.
 //              Member segments with adjacent accumulators are fused into one
 //              MMA (N up to 256) so the B panel is read from smem once per run.
@@ -285,7 +288,13 @@ __device__ __forceinline__ Item load_item(const SpmmParams& p, int it) {
 //   Cross-CTA signalling: the peer forwards "my stage is full" to the leader with a remote
 //   mbarrier arrive; stage release and accumulator-ready are tcgen05.commit multicasts;
 //   "accumulator drained" of the peer's epilogue warps is a remote arrive on the leader.
-template <bool kTf32, bool kPair>
+// kSlots = true : every pipeline stage owns a FIXED slot for its A images (a_slot_bytes, the largest
+//   chunk of the handle) next to its B panel.  No ring bookkeeping, so the producer's per-chunk
+//   instruction chain is a third as long, and a second producer warp (warp 6) can take every other
+//   chunk without sharing any state with the first.  Chosen when at least 3 such stages fit.
+// kSlots = false: the A images of the stages in flight share one byte ring (more stages in flight
+//   when chunk sizes vary a lot); single producer.
+template <bool kTf32, bool kPair, bool kSlots>
 __global__ void __launch_bounds__(kSpmmThreads, 1)
 spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -354,8 +363,75 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   const int it_end = p.cta_ptr[worker + 1];
   const bool tr = p.trace != nullptr && worker == p.trace_worker;
 
-  if (warp == 0) {
-    // ===================== TMA producer (warp 0 of every CTA, converged) =====================
+  if (kSlots && (warp == 0 || warp == 6)) {
+    // ===================== TMA producers, fixed slots (warps 0 and 6, converged) =====================
+    // Producer `my` of `step` takes the uses u = my, my + step, ... of the CTA's chunk sequence
+    // (a use = one chunk of one item, counted across items); use u lives in stage u % P.  Chunk
+    // records are fetched 32 of MY chunks at a time by the whole warp and broadcast by shuffle.
+    const uint32_t step = static_cast<uint32_t>(p.producers);
+    const uint32_t my = warp == 0 ? 0u : 1u;
+    if (my < step) {
+      const uint32_t slot_bytes = static_cast<uint32_t>(p.a_slot_bytes);
+      uint32_t u = my, slot = my % static_cast<uint32_t>(P), phase = (my / static_cast<uint32_t>(P)) & 1u;
+      uint32_t u_base = 0;   // uses of the items before this one
+      for (int it = it_begin; it < it_end; ++it) {
+        const Item item = load_item(p, it);
+        const SuperRow sr = p.srows[item.srow];
+        const int j0 = item.j0 + static_cast<int>(rank) * kTileJ;
+        const int4* recs = reinterpret_cast<const int4*>(p.chunks + sr.chunk_begin + item.chunk_off);
+        const int chunk_count = static_cast<int>(item.count & kItemCountMask);
+        const int first = static_cast<int>((my + step - (u_base % step)) % step);   // my first chunk of this item
+        const int mine_n = chunk_count > first ? (chunk_count - first + static_cast<int>(step) - 1) / static_cast<int>(step) : 0;
+        int4 nxt = make_int4(0, 0, 0, 0);
+        int2 nxt_t = make_int2(0, 0);
+        if (lane < mine_n) {
+          const int c = first + static_cast<int>(step) * lane;
+          nxt = __ldg(recs + 2 * c);
+          const int4 hi = __ldg(recs + 2 * c + 1);
+          nxt_t = make_int2(hi.y, hi.z);
+        }
+        for (int m0 = 0; m0 < mine_n; m0 += 32) {
+          const int4 cur = nxt;
+          const int2 cur_t = nxt_t;
+          if (m0 + 32 + lane < mine_n) {
+            const int c = first + static_cast<int>(step) * (m0 + 32 + lane);
+            nxt = __ldg(recs + 2 * c);
+            const int4 hi = __ldg(recs + 2 * c + 1);
+            nxt_t = make_int2(hi.y, hi.z);
+          }
+          const int batch = min(32, mine_n - m0);
+          for (int i = 0; i < batch; ++i) {
+            const int ch_k0 = __shfl_sync(0xFFFFFFFFu, cur.x, i);
+            const uint32_t ch_off16 = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.z, i));
+            const uint32_t bytes = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur.w, i)) >> kShare;
+            const uint32_t tb_bytes = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur_t.x, i));
+            const uint32_t tb_off16 = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, cur_t.y, i));
+            const unsigned long long tp0 = tr ? sm_clock() : 0ull;
+            if (u >= static_cast<uint32_t>(P)) mbar_wait(bar_empty + 8 * slot, phase ^ 1u, 1);
+            if (elect_one()) {
+              const uint32_t full = bar_full + 8 * slot;
+              const uint8_t* src = p.a_packed + static_cast<size_t>(ch_off16) * 16 + static_cast<size_t>(rank) * bytes;
+              const uint32_t dst = a_ring + slot * slot_bytes;
+              mbar_arrive_expect_tx(full, kPanelBytes + bytes + tb_bytes);
+              tma_load_2d(panels + slot * kPanelBytes, &tmap_b, ch_k0, j0, full);
+              for (uint32_t done = 0; done < bytes; done += 32768u) {
+                const uint32_t piece = min(32768u, bytes - done);
+                bulk_load(dst + done, src + done, piece, full);
+              }
+              bulk_load(tables_u + slot * kTableBytes, p.tables + static_cast<size_t>(tb_off16) * 16, tb_bytes, full);
+              if (tr) trace_put(p, true, 0, rank, u, tp0, sm_clock());
+            }
+            __syncwarp();
+            u += step;
+            slot += step;
+            if (slot >= static_cast<uint32_t>(P)) { slot -= static_cast<uint32_t>(P); phase ^= 1u; }
+          }
+        }
+        u_base += static_cast<uint32_t>(chunk_count);
+      }
+    }
+  } else if (!kSlots && warp == 0) {
+    // ===================== TMA producer, byte ring (warp 0 of every CTA, converged) =====================
     // Chunk records are fetched 32 at a time by the whole warp (one coalesced request per
     // batch, the next batch in flight while this one is issued) and broadcast by shuffle: a
     // dependent global load per chunk would cap the issue rate at one chunk per L2 round trip.
@@ -483,7 +559,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             const uint4 hdr = tbl[0];            // nruns, ksteps
             const uint4 r01 = tbl[1];            // runs 0 and 1: {idesc, where} x 2
             const uint4 r23 = tbl[2];            // runs 2 and 3 (slot is always kTableBytes long)
-            const uint32_t a_base = a_ring + starts[s];
+            const uint32_t a_base = kSlots ? a_ring + s * static_cast<uint32_t>(p.a_slot_bytes) : a_ring + starts[s];
             const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
             const int nruns = static_cast<int>(hdr.x);
             const int ksteps = static_cast<int>(hdr.y);
@@ -521,7 +597,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===================== epilogue (warps 2..5, every CTA) =====================
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -782,6 +858,41 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const SpmmParams);
+static KernelFn pick_kernel(bool tf32, bool pair, bool slots) {
+  if (slots)
+    return tf32 ? (pair ? spmm_vbr_sm100<true, true, true> : spmm_vbr_sm100<true, false, true>)
+                : (pair ? spmm_vbr_sm100<false, true, true> : spmm_vbr_sm100<false, false, true>);
+  return tf32 ? (pair ? spmm_vbr_sm100<true, true, false> : spmm_vbr_sm100<true, false, false>)
+              : (pair ? spmm_vbr_sm100<false, true, false> : spmm_vbr_sm100<false, false, false>);
+}
+
+// CTAs of the persistent grid the device can hold AT THE SAME TIME at this shared-memory
+// footprint (one per SM, in clusters of 2 in pair mode).  The in-kernel zeroing of split tiles
+// spins on a grid-wide counter, which is only safe when the whole grid is co-resident: the
+// handle clamps its grid to this number (abi.cu, create_common).
+cudaError_t spmm_max_coresident_ctas(int pair, int kind_tf32, int slots, int smem_bytes, int* out) {
+  KernelFn fn = pick_kernel(kind_tf32 != 0, pair != 0, slots != 0);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2, 1, 1);
+  cfg.blockDim = dim3(kSpmmThreads, 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int clusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&clusters, fn, &cfg);
+  if (e != cudaSuccess) return e;
+  *out = clusters * (pair ? 2 : 1);
+  return cudaSuccess;
+}
+
 cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total, int64_t ldk,
                         int precision, int grid, cudaStream_t stream, const char** err) {
   *err = "";
@@ -815,14 +926,20 @@ cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
     *err = "pair mode needs an even grid";
     return cudaErrorInvalidConfiguration;
   }
-  typedef void (*KernelFn)(const CUtensorMap, const SpmmParams);
-  KernelFn fn = p.kind_tf32 ? (p.pair ? spmm_vbr_sm100<true, true> : spmm_vbr_sm100<true, false>)
-                            : (p.pair ? spmm_vbr_sm100<false, true> : spmm_vbr_sm100<false, false>);
+  if (p.a_slot_bytes > 0 && (p.a_slot_bytes % 1024 || p.a_slot_bytes * p.panel_stages != p.a_ring_bytes)) {
+    *err = "invalid slot configuration";
+    return cudaErrorInvalidConfiguration;
+  }
+  if (p.producers < 1 || p.producers > 2 || (p.producers == 2 && p.a_slot_bytes == 0)) {
+    *err = "two copy warps need the fixed-slot pipeline";
+    return cudaErrorInvalidConfiguration;
+  }
+  KernelFn fn = pick_kernel(p.kind_tf32 != 0, p.pair != 0, p.a_slot_bytes > 0);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
-  cfg.blockDim = dim3(kSpmmThreads, 1, 1);
+  cfg.blockDim = dim3(p.producers == 2 ? kSpmmThreads : kSpmmThreads - 32, 1, 1);   // warp 6 exists only as a producer
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

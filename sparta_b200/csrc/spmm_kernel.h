@@ -27,6 +27,9 @@ struct SpmmParams {
   int32_t         acc_stage_cols; // 512 / acc_stages
   int32_t         master_col;   // > 0: TMEM column offset of the master accumulators (bounded chains)
   int32_t         pair;         // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2); cta_ptr is per pair
+  int32_t         a_slot_bytes; // > 0: fixed-slot pipeline, every stage owns this many bytes for its A images
+                                //      (a_ring_bytes = panel_stages * a_slot_bytes); 0: byte ring
+  int32_t         producers;    // copy-issuing warps per CTA: 1, or 2 (fixed slots only; alternate chunks)
   // Split pieces (kItemAtomic) add into C tiles that must start from zero.  Every CTA zeroes its
   // share of those tiles in its epilogue warps while its first item is still in the tensor pipe,
   // then bumps *sync_counter; a warp about to issue its first reduction waits until the counter
@@ -44,7 +47,7 @@ struct SpmmParams {
   int32_t         trace_cap;
 };
 
-constexpr int kSpmmThreads   = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kSpmmThreads   = 224;   // warp0 TMA, warp1 MMA, warps2-5 epilogue, warp6 second TMA producer
 constexpr int kMaxPanelStages = 8;
 constexpr int kSmemStageOff  = 3072;  // offset of the epilogue warps' staging tiles in the control block
 constexpr int kSmemCtrlBytes = 3072 + 4 * 2048;  // barriers + per-stage run tables + 4 staging tiles
@@ -62,5 +65,8 @@ static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes) {
 cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
                         int64_t ldk, int precision, int grid, cudaStream_t stream,
                         const char** err);
+
+// CTAs of the persistent grid that can be resident at the same time (see spmm_kernel.cu).
+cudaError_t spmm_max_coresident_ctas(int pair, int kind_tf32, int slots, int smem_bytes, int* out);
 
 }  // namespace sparta

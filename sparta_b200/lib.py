@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsparta_b200.so")
+# SPARTA_B200_LIB selects another build of the same ABI (A/B runs of two kernel versions on one box)
+LIB_PATH = os.environ.get("SPARTA_B200_LIB") or os.path.join(HERE, "libsparta_b200.so")
 
 BF16, FP16, TF32 = 0, 1, 2
 LAYOUT_DEFAULT, COL_MAJOR, ROW_MAJOR = 0, 1, 2
@@ -28,7 +29,8 @@ class Options(C.Structure):
         ("seg_rows", C.c_int32), ("acc_cols", C.c_int32), ("panel_stages", C.c_int32),
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
         ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
-        ("max_chain", C.c_int32), ("split_k", C.c_int32), ("fuse_rows", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("max_chain", C.c_int32), ("split_k", C.c_int32), ("fuse_rows", C.c_int32),
+        ("explicit_range", C.c_int32), ("pipeline", C.c_int32), ("copy_warps", C.c_int32), ("reserved2", C.c_int32 * 3),
     ]
 
 
@@ -98,6 +100,13 @@ SIGNATURES = {
     "sparta_host_blocking": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
                                        C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp]),
+    "sparta_grouping_save": (C.c_int, [C.c_char_p, C.c_int64, _vp, C.c_uint64]),
+    "sparta_grouping_load": (C.c_int, [C.c_char_p, C.c_int64, _vp, C.c_uint64]),
+    "sparta_blocking_key": (C.c_uint64, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
+                                         C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sparta_host_blocking_cached": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float,
+                                              C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_int32, _vp, _vp, C.POINTER(C.c_int32)]),
     "sparta_host_permutation": (C.c_int, [C.c_int64, _vp, _vp]),
     "sparta_host_partition": (C.c_int, [C.c_int64, _vp, _vp, C.POINTER(C.c_int64)]),
     "sparta_host_vbr_fill": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int32,
@@ -167,6 +176,9 @@ def make_options(precision="bf16", **kw):
         if k == "device":
             v = int(v) + 1  # ABI: 1 + ordinal, 0 = current
         setattr(o, k, int(v))
+    # a range passed from Python is literal: [0, 0) is an empty shard, not "everything"
+    if kw.get("block_row_end") is not None:
+        o.explicit_range = 1
     return o
 
 
@@ -409,6 +421,41 @@ def host_blocking(rows, cols, rowptr, colind, algo=3, tau=0.1, block_col_size=3,
     if return_stats:
         return grouping, {k: getattr(st, k) for k, _ in st._fields_}
     return grouping
+
+
+def host_blocking_cached(cache_dir, rows, cols, rowptr, colind, algo=3, tau=0.1, block_col_size=3,
+                         row_block_size=3, sim_measure=1, use_pattern=True, use_group=False,
+                         force_fixed_size=False):
+    """host_blocking behind the library's grouping cache (reference `.g` files + a key sidecar in
+    `cache_dir`).  Returns (grouping, hit)."""
+    rowptr, colind = _i64(rowptr), _i64(colind)
+    grouping = np.zeros(rows, dtype=np.int64)
+    hit = C.c_int32(0)
+    os.makedirs(cache_dir, exist_ok=True)
+    _check(load().sparta_host_blocking_cached(os.fsencode(cache_dir), rows, cols, _ptr(rowptr), _ptr(colind),
+                                              int(algo), float(tau), int(block_col_size), int(row_block_size),
+                                              int(sim_measure), int(use_pattern), int(use_group),
+                                              int(force_fixed_size), 0, _ptr(grouping), None, C.byref(hit)))
+    return grouping, bool(hit.value)
+
+
+def blocking_key(rows, cols, rowptr, colind, algo=3, tau=0.1, block_col_size=3, row_block_size=3, sim_measure=1,
+                 use_pattern=True, use_group=False, force_fixed_size=False):
+    rowptr, colind = _i64(rowptr), _i64(colind)
+    return int(load().sparta_blocking_key(rows, cols, _ptr(rowptr), _ptr(colind), int(algo), float(tau),
+                                          int(block_col_size), int(row_block_size), int(sim_measure),
+                                          int(use_pattern), int(use_group), int(force_fixed_size)))
+
+
+def grouping_save(path, grouping, key=0):
+    g = _i64(grouping)
+    _check(load().sparta_grouping_save(os.fsencode(path), len(g), _ptr(g), int(key)))
+
+
+def grouping_load(path, rows, key=0):
+    g = np.zeros(rows, dtype=np.int64)
+    _check(load().sparta_grouping_load(os.fsencode(path), rows, _ptr(g), int(key)))
+    return g
 
 
 def host_permutation(grouping):

@@ -104,6 +104,52 @@ def test_blocking_then_fill_equals_reference_vbr(lib, oracle, tmp_path):
         assert np.array_equal(v[k], res[k]), k
 
 
+def fill_matrices(tmp_path):
+    """(path, reader flags): an R-MAT pattern whose column count is NOT a multiple of any block
+    width used below (cols = 1000), and a weighted ER with empty rows and real values."""
+    r, c = synth.rmat_edges(10, 14000, seed=5)
+    keep = c < 1000
+    r, c = synth.pin_shape(r[keep], c[keep], 1024, 1000)
+    p1 = str(tmp_path / "rmat_1000.el")
+    synth.write_el(p1, r, c)
+    r, c = synth.er_edges(300, 280, 0.02, seed=11)
+    r, c = synth.pin_shape(r, c, 300, 280)
+    vals = np.random.default_rng(12).uniform(-1, 1, size=len(r)).astype(np.float32)
+    p2 = str(tmp_path / "er_weighted.el")
+    synth.write_el(p2, r, c, vals)
+    return [(p1, dict(P=1)), (p2, dict(P=0))]
+
+
+FILL_FLAG_SETS = FLAG_SETS + [
+    dict(a=5, b=7, B=9, t=0.6), dict(a=3, b=8, B=8, t=0.5, F=1), dict(a=4, b=6, B=5, t=0.7, F=1),
+    dict(a=2, b=64, B=64, F=1), dict(a=5, b=64, B=64, t=0.6, F=1),
+]
+
+
+@pytest.mark.parametrize("flags", FILL_FLAG_SETS, ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()))
+def test_vbr_fill_matches_reference(lib, oracle, tmp_path, flags):
+    """sparta_host_vbr_fill (the linear, threaded fill every benchmark matrix goes through) against
+    VBR::fill_from_CSR_inplace of the UNMODIFIED reference build (src/general/vbr.cpp:135-237;
+    the restatement where oracle/_ref is absent): row_part, nzcount, jab and mab bit for bit, over
+    every blocking flag set, weighted and pattern-only values, -F 1 row / column padding,
+    cols % w != 0, one thread and eight."""
+    from oracle.oracle_py import Reference
+    ref = Reference() if Reference.available() and flags.get("m", 1) != 2 else None
+    for path, rd in fill_matrices(tmp_path):
+        res = (ref or oracle).run(path, fill=True, **rd, **flags)
+        f = dict(b=3, B=3, F=0)
+        f.update(flags)
+        val = None if rd["P"] else res["csr_val"]
+        for threads in (1, 8):
+            v = L.host_vbr_fill(res["csr_rows"], res["csr_cols"], res["csr_rowptr"], res["csr_colind"], val,
+                                res["grouping"], f["b"], f["B"], bool(f["F"]), pattern_only=bool(rd["P"]),
+                                threads=threads)
+            for k in ("rows", "cols", "block_rows", "block_cols", "block_col_size", "nztot"):
+                assert v[k] == res[k], (path, k, threads)
+            for k in ("row_part", "nzcount", "jab", "mab"):
+                assert np.array_equal(v[k], res[k]), (path, k, threads)
+
+
 def test_invalid_arguments(lib):
     rowptr = np.array([0, 2, 3], dtype=np.int64)
     with pytest.raises(L.SpartaError):

@@ -165,9 +165,8 @@ def test_handle_api_layouts_accumulate_and_row_shards(oracle, lib):
     h.close()
     # row shards (the multi-GPU partition on one device) reassemble to the full product
     slabs = []
-    for lo, hi in ((0, 50), (50, 51), (51, 51), (51, 200)):
-        h = sparta_b200.Handle.from_csr(rows, cols, rowptr, colind, val, block_row_begin=lo,
-                                        block_row_end=hi if hi else None)
+    for lo, hi in ((0, 0), (0, 50), (50, 51), (51, 51), (51, 200)):
+        h = sparta_b200.Handle.from_csr(rows, cols, rowptr, colind, val, block_row_begin=lo, block_row_end=hi)
         if hi == lo:
             assert h.stats()["rows"] == 0
             h.close()

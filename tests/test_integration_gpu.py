@@ -54,3 +54,48 @@ def test_reference_cli_out_of_scope_mode_exits_loudly(tmp_path, lib):
                           "-B", "16", "-a", "5", "-c", "32", "-v", "0", "-o", str(tmp_path / "x.csv")],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode != 0 and "not provided" in res.stderr
+
+
+SHIM_CHECK = os.path.join(ROOT, "integration", "_ref", "shim_check")
+TEST_CUDA = os.path.join(ROOT, "integration", "_ref", "TEST_cuda_b200")
+
+
+@pytest.mark.parametrize("flags", [
+    ["-a", "5", "-b", "16", "-B", "16", "-t", "0.6"],            # -a 5: constant heights + a ragged tail block-row
+    ["-a", "3", "-b", "8", "-B", "8", "-t", "0.4"],              # variable heights
+    ["-a", "2", "-b", "16", "-B", "16", "-F", "1"],              # fixed grid, padded: also the Blocked-ELL paths
+    ["-a", "5", "-b", "32", "-B", "32", "-t", "0.6", "-F", "1"],
+])
+def test_shim_signatures_match_the_reference_cpu_multiplies(flags, lib):
+    """tests/shim_check.cpp: the reference's function signatures (cublas_fixed_blocks_multiply,
+    cublas_blockmat_batched, cublas_blockmat_multiplyBA, bellpack_*_multiplyAB,
+    cusparse_blockmat_multiplyAB) called with the reference's structs and leading dimensions, C
+    compared IN PROCESS with VBR::multiply / CSR::multiply of the unmodified reference sources."""
+    if not os.path.exists(SHIM_CHECK):
+        pytest.skip("integration/_ref/shim_check was not prebuilt (no reference checkout at build time)")
+    res = subprocess.run([SHIM_CHECK, "-f", os.path.join(ROOT, "tests", "golden", "rmat8.el"), "-P", "1", "-c", "48",
+                          "-v", "0"] + flags, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "shim_check OK" in res.stdout
+    checked = [l for l in res.stdout.splitlines() if "max_abs_diff" in l]
+    assert len(checked) >= 4 and all(l.split("max_abs_diff")[1].split()[0] == "0" for l in checked), res.stdout
+    if "-F" in flags:
+        assert any("bellpack_blockmat_multiplyAB" in l for l in checked)
+
+
+def test_reference_gpu_smoke_test_on_our_library(lib):
+    """The reference's GPU smoke test, test/cuda/TEST_cuda.cpp, UNMODIFIED on the shim with its
+    canonical flags (batch/batch_TEST_cuda:11: -b 3 -v 2 -a 2 -B 3).  Its live comparisons -- CSR
+    custom vs cusparse_blockmat_multiplyAB, Blocked-ELL vs CSR, Blocked-ELL custom vs
+    bellpack_blockmat_multiplyAB -- must print 0; the first memcmp compares against a buffer the
+    reference never fills (the cuBLAS call is commented out, TEST_cuda.cpp:117-130) and is ignored."""
+    if not os.path.exists(TEST_CUDA):
+        pytest.skip("integration/_ref/TEST_cuda_b200 was not prebuilt")
+    res = subprocess.run([TEST_CUDA, "-f", os.path.join(ROOT, "tests", "golden", "TEST_matrix_weighted.el"), "-b", "3",
+                          "-v", "0", "-a", "2", "-B", "3", "-F", "1", "-P", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    lines = [l for l in res.stdout.splitlines() if l.startswith("memcmp of")]
+    assert len(lines) == 4, res.stdout
+    for l in lines[1:]:
+        assert l.rstrip().endswith(" is 0"), res.stdout
+    assert "END" in res.stdout

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from sparta_b200 import synth
+from tests.util import random_vbr
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 with open(os.path.join(GOLDEN, "reference_vectors.json")) as f:
@@ -137,3 +138,49 @@ def test_oracle_equals_reference_build(oracle, reference, tmp_path, kind, flags)
     B = np.zeros(3 * cols + w, dtype=np.float32)
     B[:3 * cols] = rng.uniform(0, 1, size=3 * cols)
     assert np.array_equal(oracle.vbr_multiply(rr, B, 3), reference.vbr_multiply(rr, B, 3))
+
+
+def test_BA_reference_loop_literal_vs_intended(oracle):
+    """Pins the inverted product C = B*A (-M 6).  The reference has no CPU routine for it; its GPU
+    loop (cublas_blockmat_multiplyBA, src/cuda/cuda_utilities.cpp:640-690) is restated index for
+    index in oracle_ref_multiplyBA_literal (the GEMMs done in fp32 on the CPU).  Where that loop's
+    B offset `d_B + block_col_size*ib` (:645) addresses the block of B it is meant to multiply --
+    B_rows == 1 with constant heights equal to the column-block width (-b == -B), or a single
+    block-row -- the literal loop and the product the library computes (oracle_vbr_multiply_BA) are
+    the SAME numbers; elsewhere the literal loop is the intended product of a row-shifted B, which
+    is why the library implements the intended arithmetic (include/sparta_b200.h)."""
+    rng = np.random.default_rng(33)
+    # (1) B_rows = 1, h == w, several block-rows, every block-row non-empty
+    h = w = 8
+    v = random_vbr(rng, 6, 48, w, [h] * 6, 0.6, values="int", empty_rows=False)
+    Bt = rng.integers(-3, 4, size=(v["rows"], 1)).astype(np.float32)
+    lit, oor = oracle.ref_multiplyBA_literal(v, Bt, 1)
+    assert not oor
+    assert np.array_equal(lit[:v["cols"]], oracle.vbr_multiply_BA(v, Bt, 1))
+    # (2) one block-row, any B_rows and any height
+    v1 = random_vbr(rng, 1, 40, 8, [5], 0.8, values="int", empty_rows=False)
+    Bt1 = rng.integers(-3, 4, size=(5, 7)).astype(np.float32)
+    lit1, oor1 = oracle.ref_multiplyBA_literal(v1, Bt1, 7)
+    assert not oor1 and np.array_equal(lit1[:40], oracle.vbr_multiply_BA(v1, Bt1, 7))
+    # (3) B_rows = 3: the literal loop reads element w*ib + i + k*B_rows of B, i.e. it multiplies
+    # block-row ib by rows shifted w*ib down inside the first h columns.  It equals the intended
+    # product of the matrix B' whose column row_part[ib] + k holds exactly those elements.
+    m = 3
+    Bt3 = rng.integers(-3, 4, size=(v["rows"], m)).astype(np.float32)
+    lit3, oor3 = oracle.ref_multiplyBA_literal(v, Bt3, m)
+    assert not oor3
+    intended = oracle.vbr_multiply_BA(v, Bt3, m)
+    assert not np.array_equal(lit3[:v["cols"]], intended)
+    flat = Bt3.reshape(-1)     # column-major m x rows: element (i, k) at i + k*m
+    shifted = np.zeros_like(Bt3)
+    for ib in range(6):
+        for k in range(h):
+            for i in range(m):
+                shifted[h * ib + k, i] = flat[w * ib + i + k * m]
+    assert np.array_equal(lit3[:v["cols"]], oracle.vbr_multiply_BA(v, shifted, m))
+    # (4) variable heights: the loop keeps using the first block-row's height (:637) and strides mab by
+    # it (:685), so for heights that differ it walks mab out of step -- different from the intended product
+    vv = random_vbr(rng, 3, 24, 8, [8, 4, 8], 1.0, values="int", empty_rows=False)
+    Btv = rng.integers(-3, 4, size=(vv["rows"], 1)).astype(np.float32)
+    litv, _ = oracle.ref_multiplyBA_literal(vv, np.concatenate([Btv, np.zeros((16, 1), np.float32)]), 1)
+    assert not np.array_equal(litv[:24], oracle.vbr_multiply_BA(vv, Btv, 1))

@@ -84,6 +84,31 @@ def test_plan_shard_range(lib, oracle):
     assert np.array_equal(np.concatenate(pieces, axis=1), Cref)
 
 
+def test_empty_shard_is_empty(lib):
+    """A balanced partition may hand a rank nothing (cuts[1] == 0 when the first block-row outweighs
+    a whole share): an explicit [0, 0) range is an EMPTY shard, not the whole matrix; a zeroed
+    options struct (no range given) still selects everything."""
+    rng = np.random.default_rng(9)
+    heights = [256, 8, 8, 8]
+    v = random_vbr(rng, len(heights), 512, 32, heights, 1.0)
+    cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], 4)
+    assert cuts[0] == 0 and cuts[-1] == len(heights)
+    total_rows = 0
+    for i in range(4):
+        lo, hi = int(cuts[i]), int(cuts[i + 1])
+        plan = sparta_b200.vbr_plan(v["rows"], 512, 32, v["row_part"], v["nzcount"], v["jab"], 64,
+                                    block_row_begin=lo, block_row_end=hi)
+        assert plan["stats"]["rows"] == int(v["row_part"][hi] - v["row_part"][lo])
+        assert plan["stats"]["block_rows"] == hi - lo
+        total_rows += plan["stats"]["rows"]
+    assert total_rows == v["rows"]
+    empty = sparta_b200.vbr_plan(v["rows"], 512, 32, v["row_part"], v["nzcount"], v["jab"], 64,
+                                 block_row_begin=0, block_row_end=0)
+    assert empty["stats"]["rows"] == 0 and empty["stats"]["nz_blocks"] == 0 and len(empty["items"]) == 0
+    whole = sparta_b200.vbr_plan(v["rows"], 512, 32, v["row_part"], v["nzcount"], v["jab"], 64)
+    assert whole["stats"]["rows"] == v["rows"]
+
+
 def _longest_chain(chunks, srows, it):
     """MMAs the pass `it` issues into the busiest accumulator: a member's accumulator only takes
     the MMAs of the chunks it is present in (cut_passes, csrc/schedule.cpp)."""

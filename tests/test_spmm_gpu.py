@@ -378,6 +378,33 @@ BA_CASES = [
 ]
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
+@pytest.mark.parametrize("shape", [(12, 64, 64), (9, 16, 16), (1, 64, 23)])
+def test_inverted_product_equals_the_reference_loop(oracle, lib, precision, shape):
+    """The kernel against the reference's OWN loop for -M 6 (cublas_blockmat_multiplyBA,
+    src/cuda/cuda_utilities.cpp:640-690, restated index for index in the oracle) in the regime where
+    that loop's B offset is well defined: B_rows = 1 with constant heights h == w (-b == -B), and a
+    single block-row of any height (tests/test_oracle.py shows the two products coincide exactly
+    there and why they differ elsewhere).  Integer operands: exact."""
+    block_rows, w, hgt = shape
+    rng = np.random.default_rng(900 + block_rows)
+    cols = w * 11
+    v = random_vbr(rng, block_rows, cols, w, [hgt] * block_rows, 0.6, values="int", empty_rows=False)
+    m = 1 if block_rows > 1 else 37
+    Bt = rng.integers(-3, 4, size=(v["rows"], m)).astype(np.float32)
+    lit, out_of_range = oracle.ref_multiplyBA_literal(v, Bt, m)
+    assert not out_of_range
+    h = sparta_b200.Handle.from_vbr_BA(v["rows"], cols, w, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                       precision=precision)
+    try:
+        h.set_B(Bt, m, m)
+        h.run()
+        out = h.get_C(np.zeros((cols, m), np.float32), m)
+    finally:
+        h.close()
+    assert np.array_equal(out, lit[:cols])
+
+
 @pytest.mark.parametrize("mode", ["single", "pair"])
 @pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("case", range(len(BA_CASES)))
