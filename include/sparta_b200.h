@@ -80,7 +80,16 @@ typedef struct sparta_options {
   int32_t copy_warps;    /* fixed slots only: warps per CTA that issue the TMA / bulk copies, taking alternate
                             chunks.  0/2: two (default; one thread cannot start more than one pipeline stage per
                             ~600 cycles, profiles/r2_copy_issue_microbench.txt), 1: one */
-  int32_t reserved2[3];
+  int32_t gather_max_height; /* VBR handles: block-rows of at most this many rows do not go through the tensor
+                            cores (an MMA needs 8-16 rows of N; a block-row of height 1 would be 94 % padding and
+                            fetch a 16 KB panel of B to use one row of it) but through the gather kernel of the
+                            family (csr_kernel.cu) on the NONZEROS of their blocks -- same numbers, operands rounded
+                            to the handle's precision, fp32 accumulation.  0: default (7), -1: off, k > 0: heights <= k.
+                            Variable-height blockings (-a 3 / -a 4) leave most block-rows one row tall. */
+  int32_t gather_passes;  /* launches of the gather kernel per multiply, each over one range of A's columns, so that
+                            the rows of B a launch reads stay L2-resident.  0: as many as keep (columns per pass)
+                            x 256 x element size within 48 MB (default; 1 up to 2^16 columns in fp32), k > 0: k */
+  int32_t reserved2[1];
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */
@@ -104,6 +113,8 @@ typedef struct sparta_stats {
   int32_t split_pieces;    /* (piece, column tile) items that add partial sums to C (split_k) */
   int32_t zero_tiles;      /* C tiles zeroed before each launch for those pieces */
   double  sched_max_cycles; /* modelled SM cycles of the worker that finishes last */
+  int64_t gather_rows;     /* rows of the block-rows routed to the gather kernel (gather_max_height) */
+  int64_t gather_nnz;      /* their nonzeros */
 } sparta_stats;
 
 const char* sparta_last_error(void);
@@ -121,6 +132,21 @@ int sparta_device_count(void);
 int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
                       int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                       const int64_t* jab, const float* mab, const sparta_options* opt);
+
+/* A straight from the flat CSR (rowptr[rows+1], colind ascending per row, val or NULL for a pattern-only
+ * matrix) and the row grouping (one group id per row, BlockingEngine::GetGrouping): replaces
+ * VBR::fill_from_CSR_inplace (src/general/vbr.cpp:135-237) AND the upload half of the multiply routines.
+ * block_col_size / row_block_size / force_fixed_size carry the meaning of the reference's call
+ * (test/cuda/cuda_multiply.cpp:129, -b / -B / -F).  The host builds only the index arrays (identical to
+ * the reference's row_part / nzcount / jab); the dense blocks are rebuilt on the device from the
+ * nonzeros, so the fp32 mab -- 4.45 GB at BASELINE config #3 for 3.5 M nonzeros -- never exists on the
+ * host or crosses PCIe.  C rows come back in blocked order like every VBR path; dims (may be NULL)
+ * receives rows, cols, block_rows, block_cols, block_col_size, nztot of the VBR (rows / cols padded
+ * when force_fixed_size).  The options' block_row_begin / block_row_end select block-rows. */
+int sparta_vbr_create_from_csr(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                               const int64_t* colind, const float* val, const int64_t* grouping,
+                               int64_t block_col_size, int64_t row_block_size, int32_t force_fixed_size,
+                               const sparta_options* opt, int64_t* dims);
 
 /* The INVERTED product C = B*A (-M 6 / -M 11): same VBR arrays, but B is n x rows and C is
  * n x cols, both column-major with ld >= n (cuda_utilities.cpp:556-559,587-591), i.e. the handle
@@ -216,6 +242,14 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
                     const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
                     const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
                     int64_t ldc, int precision, float* dt_ms);
+
+/* The same one-shot flow from the CSR and the grouping (sparta_vbr_create_from_csr): what
+ * fill_from_CSR_inplace + cublas_fixed_blocks_multiply do together in cuda_multiply.cpp:129-137.
+ * B column-major ld = ldb >= cols (padded cols when force_fixed_size), C column-major ld = ldc >= rows. */
+int sparta_csr_vbr_spmm(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind, const float* val,
+                        const int64_t* grouping, int64_t block_col_size, int64_t row_block_size,
+                        int32_t force_fixed_size, const float* B, int64_t ldb, int64_t n, float* C, int64_t ldc,
+                        int precision, float* dt_ms);
 
 /* Replaces cublas_blockmat_multiplyBA (cuda_utilities.cpp:553-721, -M 6) and
  * cutlas_blockmat_multiplyBA (cutlass_bellpack_lib.cu:542, -M 11): C (n x cols) = B (n x rows) * A,

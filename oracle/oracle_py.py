@@ -240,11 +240,17 @@ class Reference:
     """The unmodified reference behind ref_driver.cpp; `Reference.available()` gates its use."""
 
     @staticmethod
-    def available():
-        return os.path.exists(REF_SO)
+    def available(variant=None):
+        return os.path.exists(Reference.path(variant))
 
-    def __init__(self):
-        self.lib = C.CDLL(REF_SO)
+    @staticmethod
+    def path(variant=None):
+        """variant None: the -O2 build; "O0" / "O3": the reference's own optimisation levels
+        (`make serial` has no -O flag, makefile:2; the cluster makefiles use -O3)."""
+        return REF_SO if not variant else REF_SO.replace(".so", f"_{variant}.so")
+
+    def __init__(self, variant=None):
+        self.lib = C.CDLL(Reference.path(variant))
         L = self.lib
         L.ref_run.restype = C.c_int
         L.ref_run.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(Result)]

@@ -120,6 +120,15 @@ struct sparta_handle {
   float* d_val = nullptr;
   int32_t* d_row_order = nullptr;
   int64_t nnz = 0, heavy_rows = 0;
+  // hybrid VBR handles: the block-rows of at most gather_max_height rows run on the gather kernel;
+  // their nonzeros live in the CSR arrays above (rowptr over ALL rows of the shard, the work list
+  // row_order holds the gather rows only), B is kept a second time with its ROWS contiguous
+  int64_t gather_rows = 0, gather_work = 0;   // rows routed to the gather kernel / of them with nonzeros
+  struct GatherPassDev { int64_t* beg = nullptr; int64_t* end = nullptr; int32_t* order = nullptr; int64_t work = 0, heavy = 0; };
+  std::vector<GatherPassDev> gather_passes;   // one launch per range of k (GatherPart::Pass)
+  void* d_B2 = nullptr;
+  size_t b2_cap = 0;
+  int64_t ldn2 = 0;
   void* d_B = nullptr;
   size_t b_cap = 0;
   int64_t ldk = 0, n = 0;
@@ -321,6 +330,182 @@ static const char* blockrows_from_bell(int64_t bs, int64_t ind_rows, int64_t ind
   return "";
 }
 
+// ---- short block-rows: off the tensor cores ----------------------------------------------------
+// A tcgen05.mma needs 16 rows of N (8 in single-CTA mode): a block-row of height 1 is 94 % padding
+// and pulls a 16 KB panel of B through the L2 to use one row of it per nonzero.  Variable-height
+// blockings (-a 3 / -a 4) leave most block-rows that short (BASELINE config #4: 127 586 of 137 137
+// block-rows have height 1 and hold 63 % of the stored elements).  Those block-rows are taken out
+// of the tile schedule and handed, as the nonzeros of their blocks, to the gather kernel of the
+// family (csr_kernel.cu); everything else is unchanged.  Stored zeros contribute nothing to
+// VBR::multiply (vbr.cpp:358-363), so the product is the same.
+struct GatherPart {
+  std::vector<int64_t> rowptr;    // [shard rows + 1]
+  std::vector<int32_t> colind;
+  std::vector<float> val;
+  // The nonzeros are walked in PASSES over ranges of k (columns of A = rows of B): one launch per pass,
+  // so that the part of B a pass reads -- (cols / passes) rows x 256 columns per column tile -- stays
+  // L2-resident; with one pass at 2^18 columns a tile's slab of B is 268 MB and every gathered row comes
+  // from HBM.  Pass 0 lists every gather row that has nonzeros anywhere (it WRITES the row, zeros
+  // included); later passes add to C and list only the rows with nonzeros in their range.
+  struct Pass {
+    std::vector<int64_t> beg, end;   // [shard rows]: the row's entries in this pass's range of k
+    std::vector<int32_t> order;      // work list, longest first
+    int64_t heavy = 0;               // leading entries of `order` longer than kCsrHeavyNnz
+  };
+  std::vector<Pass> passes;
+  int64_t rows = 0;               // rows of the block-rows taken out
+  int64_t nztot = 0, blocks = 0;  // their stored elements / nonzero blocks (FLOP accounting, vbr.cpp:232)
+};
+
+// The ranges of k of a gather part (GatherPart::Pass): `live` = the gather rows that hold nonzeros.
+static void build_gather_passes(GatherPart* g, const std::vector<int32_t>& live, int64_t total_rows, int64_t cols,
+                                int esize_b, int force_passes) {
+  // a pass's slab of B (range x 256 columns) within ~48 MB
+  const double slab = static_cast<double>(cols) * 256.0 * esize_b;
+  const int P = force_passes > 0 ? std::min(force_passes, 64)
+                                 : static_cast<int>(std::max(1.0, std::min(16.0, std::ceil(slab / 48e6))));
+  const int64_t range = ((cols + P - 1) / P + 63) / 64 * 64;
+  g->passes.assign(P, GatherPart::Pass());
+  for (int pi = 0; pi < P; ++pi) {
+    GatherPart::Pass& ps = g->passes[pi];
+    ps.beg.assign(static_cast<size_t>(total_rows), 0);
+    ps.end.assign(static_cast<size_t>(total_rows), 0);
+  }
+  for (int32_t r : live) {
+    int64_t at = g->rowptr[r];
+    const int64_t stop = g->rowptr[r + 1];
+    for (int pi = 0; pi < P; ++pi) {
+      const int64_t k_hi = (pi + 1 == P) ? cols : (pi + 1) * range;
+      const int64_t first = at;
+      while (at < stop && g->colind[at] < k_hi) ++at;     // columns ascend inside a row
+      g->passes[pi].beg[r] = first;
+      g->passes[pi].end[r] = at;
+    }
+  }
+  for (int pi = 0; pi < P; ++pi) {
+    GatherPart::Pass& ps = g->passes[pi];
+    for (int32_t r : live)
+      if (pi == 0 || ps.end[r] > ps.beg[r]) ps.order.push_back(r);
+    std::stable_sort(ps.order.begin(), ps.order.end(),
+                     [&](int32_t a, int32_t c) { return ps.end[a] - ps.beg[a] > ps.end[c] - ps.beg[c]; });
+    ps.heavy = 0;
+    while (ps.heavy < static_cast<int64_t>(ps.order.size()) &&
+           ps.end[ps.order[ps.heavy]] - ps.beg[ps.order[ps.heavy]] > kCsrHeavyNnz)
+      ++ps.heavy;
+  }
+}
+
+static bool split_short_block_rows(const BlockRows& br, int max_height, const float* src, int64_t cols,
+                                   int esize_b, int force_passes, BlockRows* tall, GatherPart* g) {
+  const int64_t nb = br.count();
+  if (max_height <= 0 || nb == 0 || !br.blk_k0.empty() || !br.sub_ptr.empty()) return false;
+  std::vector<int64_t> shorts;
+  for (int64_t b = 0; b < nb; ++b)
+    if (br.height[b] > 0 && br.height[b] <= max_height && br.ptr[b + 1] > br.ptr[b]) shorts.push_back(b);
+  if (shorts.empty()) return false;
+  int64_t total_rows = 0;
+  for (int64_t b = 0; b < nb; ++b) total_rows = std::max(total_rows, br.row0[b] + br.height[b]);
+  if (total_rows > INT32_MAX || cols > INT32_MAX) return false;
+  // the tall view: same rows of C, same sources, the short block-rows dropped
+  BlockRows t;
+  t.w = br.w;
+  t.ptr.push_back(0);
+  {
+    size_t si = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+      if (si < shorts.size() && shorts[si] == b) { ++si; continue; }
+      t.row0.push_back(br.row0[b]); t.height.push_back(br.height[b]); t.rs.push_back(br.rs[b]); t.ks.push_back(br.ks[b]);
+      for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) { t.col.push_back(br.col[q]); t.src.push_back(br.src[q]); }
+      t.ptr.push_back(static_cast<int64_t>(t.col.size()));
+    }
+  }
+  // nonzeros of the short block-rows, scanned by all host threads over contiguous ranges of them
+  unsigned hw = std::thread::hardware_concurrency();
+  const int T = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::min(hw ? hw : 8u, 32u), shorts.size() / 64 + 1)));
+  std::vector<std::vector<int32_t>> t_col(T);
+  std::vector<std::vector<float>> t_val(T);
+  std::vector<int64_t> row_nnz(static_cast<size_t>(total_rows), 0);
+  auto work = [&](int tid) {
+    const size_t lo = shorts.size() * tid / T, hi = shorts.size() * (tid + 1) / T;
+    std::vector<int32_t>& cv = t_col[tid];
+    std::vector<float>& vv = t_val[tid];
+    for (size_t si = lo; si < hi; ++si) {
+      const int64_t b = shorts[si];
+      const int64_t H = br.height[b], rs = br.rs[b], ks = br.ks[b];
+      for (int64_t r = 0; r < H; ++r) {
+        int64_t cnt = 0;
+        for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) {
+          const float* blk = src + br.src[q] + r * rs;
+          const int64_t k0 = br.col[q] * br.w;
+          const int64_t kw = std::min<int64_t>(br.w, cols - k0);
+          for (int64_t c = 0; c < kw; ++c) {
+            const float x = blk[c * ks];
+            if (x != 0.0f) { cv.push_back(static_cast<int32_t>(k0 + c)); vv.push_back(x); ++cnt; }
+          }
+        }
+        row_nnz[static_cast<size_t>(br.row0[b] + r)] = cnt;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int tid = 1; tid < T; ++tid) th.emplace_back(work, tid);
+  work(0);
+  for (auto& x : th) x.join();
+  g->rowptr.assign(static_cast<size_t>(total_rows) + 1, 0);
+  for (int64_t r = 0; r < total_rows; ++r) g->rowptr[r + 1] = g->rowptr[r] + row_nnz[r];
+  const int64_t nnz = g->rowptr[total_rows];
+  g->colind.resize(static_cast<size_t>(nnz));
+  g->val.resize(static_cast<size_t>(nnz));
+  {
+    // thread t's entries are the rows of its block-rows in order: copy them behind each other
+    // (the short block-rows are visited in ascending row order, and rowptr was built the same way)
+    int64_t at = 0;
+    for (int tid = 0; tid < T; ++tid) {
+      std::copy(t_col[tid].begin(), t_col[tid].end(), g->colind.begin() + at);
+      std::copy(t_val[tid].begin(), t_val[tid].end(), g->val.begin() + at);
+      at += static_cast<int64_t>(t_col[tid].size());
+    }
+  }
+  g->rows = 0; g->nztot = 0; g->blocks = 0;
+  std::vector<int32_t> live;      // gather rows that hold nonzeros
+  for (int64_t b : shorts) {
+    g->rows += br.height[b];
+    g->blocks += br.ptr[b + 1] - br.ptr[b];
+    g->nztot += (br.ptr[b + 1] - br.ptr[b]) * br.height[b] * br.w;
+    for (int64_t r = 0; r < br.height[b]; ++r)
+      if (row_nnz[static_cast<size_t>(br.row0[b] + r)] > 0) live.push_back(static_cast<int32_t>(br.row0[b] + r));
+  }
+  build_gather_passes(g, live, total_rows, cols, esize_b, force_passes);
+  *tall = std::move(t);
+  return true;
+}
+
+
+// The same split on the index arrays alone (no values at hand: partition requests): the tall view
+// and an ESTIMATE of the gather rows' nonzeros -- blocks of a short block-row of a clustered sparse
+// matrix hold little more than one nonzero per row.
+static bool split_short_view(const BlockRows& br, int max_height, BlockRows* tall, double* est_nnz) {
+  const int64_t nb = br.count();
+  *est_nnz = 0;
+  if (max_height <= 0 || nb == 0 || !br.blk_k0.empty() || !br.sub_ptr.empty()) return false;
+  BlockRows t;
+  t.w = br.w;
+  t.ptr.push_back(0);
+  bool any = false;
+  for (int64_t b = 0; b < nb; ++b) {
+    if (br.height[b] > 0 && br.height[b] <= max_height && br.ptr[b + 1] > br.ptr[b]) {
+      *est_nnz += 1.2 * static_cast<double>(br.ptr[b + 1] - br.ptr[b]) * static_cast<double>(br.height[b]);
+      any = true;
+      continue;
+    }
+    t.row0.push_back(br.row0[b]); t.height.push_back(br.height[b]); t.rs.push_back(br.rs[b]); t.ks.push_back(br.ks[b]);
+    for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) { t.col.push_back(br.col[q]); t.src.push_back(br.src[q]); }
+    t.ptr.push_back(static_cast<int64_t>(t.col.size()));
+  }
+  if (any) *tall = std::move(t);
+  return any;
+}
+
 // ---- handle construction ---------------------------------------------------
 
 static void free_handle(sparta_handle* h) {
@@ -331,7 +516,8 @@ static void free_handle(sparta_handle* h) {
     dev_free(h->d_segs, s); dev_free(h->d_srows, s); dev_free(h->d_chunks, s); dev_free(h->d_tables, s);
     dev_free(h->d_a, s); dev_free(h->d_items, s); dev_free(h->d_cta_ptr, s); dev_free(h->d_cta_items, s); dev_free(h->d_zero_jobs, s); dev_free(h->d_sync, s);
     dev_free(h->d_rowptr, s); dev_free(h->d_colind, s); dev_free(h->d_val, s); dev_free(h->d_row_order, s);
-    dev_free(h->d_B, s); dev_free(h->d_C, s);
+    dev_free(h->d_B, s); dev_free(h->d_B2, s); dev_free(h->d_C, s);
+    for (auto& gp : h->gather_passes) { dev_free(gp.beg, s); dev_free(gp.end, s); dev_free(gp.order, s); }
     cudaStreamSynchronize(s);   // the blocks are back in the pool before the stream goes away
   }
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -448,7 +634,7 @@ static bool scan_nonzeros(const float* src, int64_t n, SparseSource* out) {
 // get_C are enqueued behind the upload on the handle's stream.
 static int create_common(sparta_handle** out, BlockRows& br, const float* src_host,
                          int64_t src_elems, int64_t cols, const sparta_options& o,
-                         int default_row_major, bool defer_sync = false) {
+                         int default_row_major, bool defer_sync = false, const SparseSource* pre = nullptr) {
   *out = nullptr;
   if (o.panel_stages < 2 || o.panel_stages > kMaxPanelStages)
     return fail(SPARTA_ERR_INVALID, "invalid panel_stages");
@@ -526,7 +712,28 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
     // says the source is sparse, the host threads pick out the nonzeros (a read of the array at
     // memory speed), only those cross PCIe, and the dense image is rebuilt on the device.
     SparseSource sp;
-    if (src_elems >= (int64_t{1} << 22) && !getenv("SPARTA_DENSE_UPLOAD") &&
+    if (pre) {
+      // the caller already holds the nonzeros (built from the CSR): only they cross PCIe
+      sparse_upload = true;
+      H_TRY(cudaMemsetAsync(d_src, 0, static_cast<size_t>(src_elems) * sizeof(float), h->stream));
+      if (pre->total > 0) {
+        H_TRY(dev_alloc(&d_idx, static_cast<size_t>(pre->total) * sizeof(int64_t), h->stream));
+        H_TRY(dev_alloc(&d_val, static_cast<size_t>(pre->total) * sizeof(float), h->stream));
+        int64_t at = 0;
+        for (size_t t = 0; t < pre->idx.size(); ++t) {
+          const size_t cnt = pre->idx[t].size();
+          if (!cnt) continue;
+          H_TRY(cudaMemcpyAsync(d_idx + at, pre->idx[t].data(), cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+          H_TRY(cudaMemcpyAsync(d_val + at, pre->val[t].data(), cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+          at += static_cast<int64_t>(cnt);
+        }
+        H_TRY(scatter_values(d_idx, d_val, pre->total, d_src, h->stream));
+        dev_free(d_idx, h->stream);
+        dev_free(d_val, h->stream);
+        d_idx = nullptr;
+        d_val = nullptr;
+      }
+    } else if (src_elems >= (int64_t{1} << 22) && !getenv("SPARTA_DENSE_UPLOAD") &&
         sampled_density(src_host, src_elems) < 0.10) {
       // With a pinned source the copy engine and the host threads work at the same time: the head
       // of the array crosses PCIe as it is (the DMA runs at ~46 GB/s) while the threads scan the
@@ -632,6 +839,143 @@ int sparta_device_count(void) {
   return ok;
 }
 
+// Uploads the gather rows of a hybrid handle (values rounded to the operand precision on the device).
+// On failure the handle is freed.
+static int attach_gather(sparta_handle* h, const GatherPart& gp, int precision) {
+  cudaError_t e = upload_vec(gp.colind, &h->d_colind, h->stream);
+  if (e == cudaSuccess) e = upload_vec(gp.val, &h->d_val, h->stream);
+  h->gather_passes.assign(gp.passes.size(), sparta_handle::GatherPassDev());
+  for (size_t pi = 0; pi < gp.passes.size() && e == cudaSuccess; ++pi) {
+    sparta_handle::GatherPassDev& d = h->gather_passes[pi];
+    e = upload_vec(gp.passes[pi].beg, &d.beg, h->stream);
+    if (e == cudaSuccess) e = upload_vec(gp.passes[pi].end, &d.end, h->stream);
+    if (e == cudaSuccess) e = upload_vec(gp.passes[pi].order, &d.order, h->stream);
+    d.work = static_cast<int64_t>(gp.passes[pi].order.size());
+    d.heavy = gp.passes[pi].heavy;
+  }
+  if (e == cudaSuccess) e = round_values(h->d_val, static_cast<int64_t>(gp.val.size()), precision, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // the host vectors go away
+  if (e != cudaSuccess) { free_handle(h); return fail_cuda(e, "upload of the gather rows"); }
+  h->gather_rows = gp.rows;
+  h->gather_work = gp.passes.empty() ? 0 : static_cast<int64_t>(gp.passes[0].order.size());
+  h->nnz = static_cast<int64_t>(gp.val.size());
+  h->st.nztot += gp.nztot;
+  h->st.n_blocks += gp.blocks;
+  return SPARTA_OK;
+}
+
+// A straight from the flat CSR and the row grouping: VBR::fill_from_CSR_inplace (vbr.cpp:135-237) and
+// the upload half of the multiply routines in one step.  The host only builds the INDEX arrays
+// (row_part / nzcount / jab, bit-identical to the reference's) and the element offset every nonzero
+// would have in mab; the dense blocks are rebuilt on the device from those (offset, value) pairs and
+// packed there.  BASELINE config #3: 3.5 M nonzeros = 42 MB over PCIe instead of a 4.45 GB mab that is
+// 99.7 % zeros.  The gather rows of a hybrid handle are CSR rows as they are.
+static int vbr_create_from_csr_impl(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                                    const int64_t* colind, const float* val, const int64_t* grouping,
+                                    int64_t block_col_size, int64_t row_block_size, int32_t force_fixed_size,
+                                    const sparta_options* opt, bool defer_sync, HostVBR* index_out) {
+  if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (rows <= 0 || cols <= 0 || !rowptr || !grouping || (rowptr[rows] && !colind) || block_col_size <= 0)
+    return fail(SPARTA_ERR_INVALID, "invalid CSR input");
+  sparta_options o;
+  resolve_options(opt, &o);
+  unsigned hw = std::thread::hardware_concurrency();
+  const int threads = static_cast<int>(std::max(1u, std::min(hw ? hw : 8u, 32u)));
+  HostVBRSparse hv;
+  const char* e = host_vbr_fill_sparse(rows, cols, rowptr, colind, val, val == nullptr, grouping, block_col_size,
+                                       row_block_size, force_fixed_size != 0, threads, &hv);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  const HostVBR& ix = hv.index;
+  const int64_t lo = o.block_row_begin;
+  const int64_t hi = range_end(o, ix.block_rows);
+  BlockRows br;
+  int64_t src_lo = 0, src_hi = 0;
+  e = blockrows_from_vbr(ix.block_rows, block_col_size, ix.row_part.data(), ix.nzcount.data(), ix.jab.data(), lo, hi,
+                         &br, &src_lo, &src_hi);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  const int64_t shard_rows = ix.row_part[hi] - ix.row_part[lo];
+  // gather rows: the CSR rows of the short block-rows, as they are
+  const int gather_h = o.gather_max_height < 0 ? 0 : (o.gather_max_height == 0 ? 7 : o.gather_max_height);
+  std::vector<char> is_short(static_cast<size_t>(hi - lo), 0);
+  GatherPart gp;
+  bool hybrid = false;
+  if (gather_h > 0 && shard_rows <= INT32_MAX && ix.cols <= INT32_MAX) {
+    gp.rowptr.assign(static_cast<size_t>(shard_rows) + 1, 0);
+    std::vector<int32_t> live;
+    for (int64_t b = lo; b < hi; ++b) {
+      const int64_t H = ix.row_part[b + 1] - ix.row_part[b];
+      if (H <= 0 || H > gather_h || ix.nzcount[b] == 0) continue;
+      is_short[static_cast<size_t>(b - lo)] = 1;
+      hybrid = true;
+      gp.rows += H;
+      gp.blocks += ix.nzcount[b];
+      gp.nztot += ix.nzcount[b] * H * block_col_size;
+    }
+    if (hybrid) {
+      for (int64_t b = lo; b < hi; ++b) {
+        for (int64_t r = ix.row_part[b]; r < ix.row_part[b + 1]; ++r) {
+          int64_t cnt = 0;
+          if (is_short[static_cast<size_t>(b - lo)] && r < rows) cnt = rowptr[hv.perm[r] + 1] - rowptr[hv.perm[r]];
+          gp.rowptr[static_cast<size_t>(r - ix.row_part[lo]) + 1] = cnt;
+        }
+      }
+      for (int64_t r = 0; r < shard_rows; ++r) gp.rowptr[r + 1] += gp.rowptr[r];
+      gp.colind.resize(static_cast<size_t>(gp.rowptr[shard_rows]));
+      gp.val.resize(gp.colind.size());
+      for (int64_t b = lo; b < hi; ++b) {
+        if (!is_short[static_cast<size_t>(b - lo)]) continue;
+        for (int64_t r = ix.row_part[b]; r < ix.row_part[b + 1] && r < rows; ++r) {
+          const int64_t i = hv.perm[r], local = r - ix.row_part[lo];
+          int64_t at = gp.rowptr[local];
+          for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p, ++at) {
+            gp.colind[at] = static_cast<int32_t>(colind[p]);
+            gp.val[at] = val ? val[p] : 1.0f;
+          }
+          if (rowptr[i + 1] > rowptr[i]) live.push_back(static_cast<int32_t>(local));
+        }
+      }
+      build_gather_passes(&gp, live, shard_rows, ix.cols, prec_esize(o.precision), o.gather_passes);
+    }
+  }
+  // the tile schedule's view: the tall block-rows; its nonzeros: (offset relative to the shard, value)
+  BlockRows tall;
+  if (hybrid) {
+    tall.w = br.w;
+    tall.ptr.push_back(0);
+    for (int64_t b = 0; b < br.count(); ++b) {
+      if (is_short[static_cast<size_t>(b)]) continue;
+      tall.row0.push_back(br.row0[b]); tall.height.push_back(br.height[b]); tall.rs.push_back(br.rs[b]); tall.ks.push_back(br.ks[b]);
+      for (int64_t q = br.ptr[b]; q < br.ptr[b + 1]; ++q) { tall.col.push_back(br.col[q]); tall.src.push_back(br.src[q]); }
+      tall.ptr.push_back(static_cast<int64_t>(tall.col.size()));
+    }
+  }
+  SparseSource pre;
+  pre.idx.assign(1, {});
+  pre.val.assign(1, {});
+  for (int64_t b = lo; b < hi; ++b) {
+    if (is_short[static_cast<size_t>(b - lo)]) continue;
+    for (int64_t q = hv.nz_ptr[b]; q < hv.nz_ptr[b + 1]; ++q) {
+      pre.idx[0].push_back(hv.nz_off[q] - src_lo);
+      pre.val[0].push_back(hv.nz_val[q]);
+    }
+  }
+  pre.total = static_cast<int64_t>(pre.idx[0].size());
+  const int rc = create_common(out, hybrid ? tall : br, nullptr, src_hi - src_lo, ix.cols, o, 0, false, &pre);
+  if (rc != SPARTA_OK) return rc;
+  (void)defer_sync;   // the nonzero lists above are locals: the upload is complete when this returns
+  sparta_handle* h = *out;
+  h->rows = shard_rows;
+  h->st.rows = shard_rows;
+  h->block_rows = hi - lo;
+  if (hybrid) {
+    const int grc = attach_gather(h, gp, o.precision);
+    if (grc != SPARTA_OK) { *out = nullptr; return grc; }
+  }
+  if (index_out) *index_out = std::move(hv.index);
+  return SPARTA_OK;
+}
+
 static int vbr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
                            int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                            const int64_t* jab, const float* mab, const sparta_options* opt,
@@ -654,13 +998,43 @@ static int vbr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int6
   for (int64_t jb : br.col)
     if (jb >= bc) return fail(SPARTA_ERR_INVALID, "jab entry beyond the last column block");
   if (src_hi > src_lo && !mab) return fail(SPARTA_ERR_INVALID, "mab is NULL");
-  return create_common(out, br, mab ? mab + src_lo : nullptr, src_hi - src_lo, cols, o, 0, defer_sync);
+  const int gather_h = o.gather_max_height < 0 ? 0 : (o.gather_max_height == 0 ? 7 : o.gather_max_height);
+  BlockRows tall;
+  GatherPart gp;
+  const bool hybrid = mab && split_short_block_rows(br, gather_h, mab + src_lo, cols, prec_esize(o.precision), o.gather_passes, &tall, &gp);
+  const int64_t shard_rows = row_part[hi] - row_part[lo];
+  const int rc = create_common(out, hybrid ? tall : br, mab ? mab + src_lo : nullptr, src_hi - src_lo, cols, o, 0,
+                               defer_sync && !hybrid);
+  if (rc != SPARTA_OK) return rc;
+  sparta_handle* h = *out;
+  h->rows = shard_rows;           // the tile schedule may not reach the last rows any more
+  h->st.rows = shard_rows;
+  h->block_rows = hi - lo;
+  if (hybrid) {
+    const int grc = attach_gather(h, gp, o.precision);
+    if (grc != SPARTA_OK) { *out = nullptr; return grc; }
+  }
+  return SPARTA_OK;
 }
 
 int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
                       int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                       const int64_t* jab, const float* mab, const sparta_options* opt) {
   return vbr_create_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false);
+}
+
+int sparta_vbr_create_from_csr(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
+                               const int64_t* colind, const float* val, const int64_t* grouping,
+                               int64_t block_col_size, int64_t row_block_size, int32_t force_fixed_size,
+                               const sparta_options* opt, int64_t* dims) {
+  HostVBR ix;
+  const int rc = vbr_create_from_csr_impl(out, rows, cols, rowptr, colind, val, grouping, block_col_size,
+                                          row_block_size, force_fixed_size, opt, false, &ix);
+  if (rc == SPARTA_OK && dims) {
+    dims[0] = ix.rows; dims[1] = ix.cols; dims[2] = ix.block_rows; dims[3] = ix.block_cols;
+    dims[4] = ix.block_col_size; dims[5] = ix.nztot;
+  }
+  return rc;
 }
 
 static int vbr_create_ba_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
@@ -862,6 +1236,22 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
                     h->stream, /*keep_fp32=*/h->sopt.precision == PREC_TF32);
   } else {
     e = convert_b(src, src_ld, h->b_row_major, h->d_B, ldk, h->cols, n, h->sopt.precision, h->stream, false);
+    if (e == cudaSuccess && h->gather_work > 0) {
+      // the gather rows read ROWS of B: a second copy [cols][ldn] in the operand precision (tf32:
+      // 4-byte values rounded like the tensor-core operand)
+      const int64_t ldn = (n + 7) / 8 * 8;
+      const size_t b2 = static_cast<size_t>(h->cols) * ldn * prec_esize(h->sopt.precision);
+      if (b2 > h->b2_cap) {
+        dev_free(h->d_B2, h->stream);
+        h->b2_cap = 0;
+        e = dev_alloc(&h->d_B2, b2, h->stream);
+        if (e == cudaSuccess) h->b2_cap = b2;
+      }
+      if (e == cudaSuccess && ldn != n) e = cudaMemsetAsync(h->d_B2, 0, b2, h->stream);
+      if (e == cudaSuccess)
+        e = convert_b(src, src_ld, !h->b_row_major, h->d_B2, ldn, n, h->cols, h->sopt.precision, h->stream, false);
+      h->ldn2 = ldn;
+    }
   }
   dev_free(d_stage, h->stream);
   if (e != cudaSuccess) return fail_cuda(e, "B conversion");
@@ -995,7 +1385,29 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
     if (h->rows > 0) ++h->launches;
     return SPARTA_OK;
   }
-  if (h->as.grid == 0) return SPARTA_OK;  // empty shard: nothing to compute
+  if (h->gather_work > 0) {
+    // the short block-rows of a hybrid handle (disjoint rows of C, same stream)
+    if (trace) return fail(SPARTA_ERR_INVALID, "worker timelines need a handle without gather rows (gather_max_height = -1)");
+    for (size_t pi = 0; pi < h->gather_passes.size(); ++pi) {
+      const sparta_handle::GatherPassDev& d = h->gather_passes[pi];
+      if (d.work == 0) continue;
+      CsrParams c;
+      memset(&c, 0, sizeof(c));
+      c.rowptr = d.beg; c.rowend = d.end; c.colind = h->d_colind; c.val = h->d_val; c.row_order = d.order;
+      c.B = h->d_B2; c.C = h->d_C;
+      c.c_sr = h->c_row_major ? h->ldc : 1;
+      c.c_sj = h->c_row_major ? 1 : h->ldc;
+      c.rows = d.work;
+      c.heavy_rows = d.heavy;
+      c.n = static_cast<int32_t>(h->n);
+      c.ldn = static_cast<int32_t>(h->ldn2);
+      c.accumulate = pi == 0 ? h->accumulate : 1;   // pass 0 writes the rows, the later ranges of k add to them
+      const cudaError_t e = spmm_csr_launch(c, h->sopt.precision, h->stream);
+      if (e != cudaSuccess) return fail_cuda(e, "gather kernel launch");
+      ++h->launches;
+    }
+  }
+  if (h->as.grid == 0) return SPARTA_OK;  // empty shard / nothing for the tensor cores
   SpmmParams p;
   memset(&p, 0, sizeof(p));
   p.items = h->d_items; p.cta_ptr = h->d_cta_ptr; p.cta_items = h->d_cta_items;
@@ -1138,6 +1550,12 @@ int sparta_get_stats(sparta_handle* h, sparta_stats* out) {
   else
     cudaGetLastError();
   out->kernel_launches = h->launches;
+  if (h->kind == 0) {
+    out->gather_rows = h->gather_rows;
+    out->gather_nnz = h->gather_work > 0 ? h->nnz : 0;
+    out->block_rows = h->block_rows;
+    if (h->gather_work > 0) out->b_bytes += h->cols * h->ldn2 * prec_esize(h->sopt.precision);
+  }
   return SPARTA_OK;
 }
 
@@ -1198,6 +1616,20 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
   o.precision = precision;
   return one_shot("sparta_vbr_spmm", [&](sparta_handle** h) {
     return vbr_create_impl(h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o, true);
+  }, B, ldb, n, C, ldc, dt_ms);
+}
+
+int sparta_csr_vbr_spmm(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind, const float* val,
+                        const int64_t* grouping, int64_t block_col_size, int64_t row_block_size,
+                        int32_t force_fixed_size, const float* B, int64_t ldb, int64_t n, float* C, int64_t ldc,
+                        int precision, float* dt_ms) {
+  sparta_options o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  o.precision = precision;
+  return one_shot("sparta_csr_vbr_spmm", [&](sparta_handle** h) {
+    return vbr_create_from_csr_impl(h, rows, cols, rowptr, colind, val, grouping, block_col_size, row_block_size,
+                                    force_fixed_size, &o, true, nullptr);
   }, B, ldb, n, C, ldc, dt_ms);
 }
 
@@ -1344,12 +1776,22 @@ static int partition_modelled_impl(int64_t rows, int64_t cols, int64_t block_row
                                          &br, &src_lo, &src_hi);
       Structure st;
       Assignment as;
-      BlockRows fused;
-      const bool use_fused = !*e && o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused);
-      if (!*e) e = build_structure(use_fused ? fused : br, so, &st);
+      BlockRows fused, tall;
+      double gather_nnz = 0;
+      const int gather_h = o.gather_max_height < 0 ? 0 : (o.gather_max_height == 0 ? 7 : o.gather_max_height);
+      const BlockRows* view = &br;
+      if (!*e && split_short_view(br, gather_h, &tall, &gather_nnz)) view = &tall;
+      const bool use_fused = !*e && o.fuse_rows != 1 && fuse_short_block_rows(*view, 16, &fused);
+      if (!*e) e = build_structure(use_fused ? fused : *view, so, &st);
       if (!*e) e = build_assignment(st, so, n, cols, &as);
       if (*e) return fail(SPARTA_ERR_INVALID, e);
-      t[i] = as.max_cta_cost;
+      // the gather rows run before the tile schedule on the same stream: one row of B (n elements) per
+      // nonzero through the L2 at ~40 bytes per clock and SM (HBM speed when a column tile's slab of B,
+      // cols x 256 elements, is larger than the L2)
+      const double esb = so.precision == PREC_TF32 ? 4.0 : 2.0;
+      const double slab = static_cast<double>(cols) * 256.0 * esb;
+      const double rate = so.num_ctas * (slab > 100e6 ? 20.0 : 40.0);
+      t[i] = as.max_cta_cost + gather_nnz * static_cast<double>(n) * esb / rate;
       if (time_scale) {
         double ws = 0, w = 0;
         for (int64_t b = cur[i]; b < cur[i + 1]; ++b) { ws += weight[b] * time_scale[b]; w += weight[b]; }

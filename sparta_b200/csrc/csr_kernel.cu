@@ -161,7 +161,7 @@ spmm_csr_sm100(const CsrParams p) {
 
   if (static_cast<int64_t>(blockIdx.x) < p.heavy_rows) {
     const int32_t row = p.row_order[blockIdx.x];
-    const int64_t beg = p.rowptr[row], end = p.rowptr[row + 1];
+    const int64_t beg = p.rowptr[row], end = p.rowend ? p.rowend[row] : p.rowptr[row + 1];
     const int64_t per = (end - beg + (kCsrThreads / 32) - 1) / (kCsrThreads / 32);
     const int64_t b = min(end, beg + warp * per), e = min(end, b + per);
     row_slice<kPrec>(p, b, e, j0, live, lane, acc);
@@ -182,7 +182,7 @@ spmm_csr_sm100(const CsrParams p) {
   const int64_t slot = p.heavy_rows + (static_cast<int64_t>(blockIdx.x) - p.heavy_rows) * (kCsrThreads / 32) + warp;
   if (slot >= p.rows) return;
   const int32_t row = p.row_order[slot];
-  row_slice<kPrec>(p, p.rowptr[row], p.rowptr[row + 1], j0, live, lane, acc);
+  row_slice<kPrec>(p, p.rowptr[row], p.rowend ? p.rowend[row] : p.rowptr[row + 1], j0, live, lane, acc);
   if (live) store8(p, row, j0, acc);
 }
 

@@ -7,7 +7,8 @@
 namespace sparta {
 
 struct CsrParams {
-  const int64_t* rowptr;     // [rows + 1]
+  const int64_t* rowptr;     // [rows + 1]: row r owns entries [rowptr[r], rowptr[r + 1]) ...
+  const int64_t* rowend;     // ... or [rowptr[r], rowend[r]) when rowend is given (a column range of the rows)
   const int32_t* colind;     // [nnz], ascending inside a row like the reference's CSR
   const float*   val;        // [nnz] (ones for pattern-only matrices, csr.cpp:59)
   const int32_t* row_order;  // rows in descending-nnz order (host, stable)

@@ -53,12 +53,19 @@ static void parallel_for(int64_t n, int threads, F fn) {
   for (auto& th : pool) th.join();
 }
 
-const char* host_vbr_fill(int64_t rows_in, int64_t cols_in, const int64_t* rowptr,
-                          const int64_t* colind, const float* val, bool pattern_only,
-                          const int64_t* grouping, int64_t w, int64_t row_block_size,
-                          bool force_fixed, int threads, HostVBR* out) {
+// dense: the reference's arrays, mab included.  sparse != nullptr: mab is NOT built; the nonzeros go to
+// sparse->nz_* as (offset into the virtual mab, value) and the permutation is kept.
+static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t* rowptr,
+                                 const int64_t* colind, const float* val, bool pattern_only,
+                                 const int64_t* grouping, int64_t w, int64_t row_block_size,
+                                 bool force_fixed, int threads, HostVBR* out, HostVBRSparse* sparse) {
   if (w <= 0) return "column block size must be positive";
   if (force_fixed && row_block_size <= 0) return "force_fixed needs a positive row block size";
+  for (int64_t i = 0; i < rows_in; ++i) {
+    if (rowptr[i + 1] < rowptr[i]) return "rowptr must be non-decreasing";
+    for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
+      if (colind[p] < 0 || colind[p] >= cols_in) return "column index out of range";
+  }
   std::vector<int64_t> perm(rows_in), part(rows_in + 1);
   host_permutation(grouping, rows_in, perm.data());
   part.resize(host_partition(grouping, rows_in, part.data()));
@@ -104,7 +111,18 @@ const char* host_vbr_fill(int64_t rows_in, int64_t cols_in, const int64_t* rowpt
   }
   out->jab.resize(jab_off[block_rows]);
   out->nztot = mab_off[block_rows];
-  out->mab.assign(static_cast<size_t>(out->nztot), 0.0f);
+  if (sparse) {
+    sparse->nz_ptr.assign(block_rows + 1, 0);
+    for (int64_t ib = 0; ib < block_rows; ++ib) {
+      int64_t cnt = 0;
+      for (int64_t r = part[ib]; r < part[ib + 1] && r < rows_in; ++r) cnt += rowptr[perm[r] + 1] - rowptr[perm[r]];
+      sparse->nz_ptr[ib + 1] = sparse->nz_ptr[ib] + cnt;
+    }
+    sparse->nz_off.resize(static_cast<size_t>(sparse->nz_ptr[block_rows]));
+    sparse->nz_val.resize(static_cast<size_t>(sparse->nz_ptr[block_rows]));
+  } else {
+    out->mab.assign(static_cast<size_t>(out->nztot), 0.0f);
+  }
 
   // pass 2: scatter values; block (ib, slot) is column-major with ld = h (vbr.cpp:224)
   parallel_for(block_rows, threads, [&](int64_t lo, int64_t hi) {
@@ -114,18 +132,43 @@ const char* host_vbr_fill(int64_t rows_in, int64_t cols_in, const int64_t* rowpt
       std::copy(list.begin(), list.end(), out->jab.begin() + jab_off[ib]);
       for (size_t s = 0; s < list.size(); ++s) slot[list[s]] = static_cast<int64_t>(s);
       const int64_t h = part[ib + 1] - part[ib];
-      float* base = out->mab.data() + mab_off[ib];
+      float* base = sparse ? nullptr : out->mab.data() + mab_off[ib];
+      int64_t at = sparse ? sparse->nz_ptr[ib] : 0;
       for (int64_t r = part[ib]; r < part[ib + 1]; ++r) {
         if (r >= rows_in) break;
         const int64_t i = perm[r];
         for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
           const int64_t j = colind[p];
-          base[slot[j / w] * w * h + h * (j % w) + (r - part[ib])] = pattern_only ? 1.0f : val[p];
+          const int64_t off = slot[j / w] * w * h + h * (j % w) + (r - part[ib]);
+          const float x = pattern_only ? 1.0f : val[p];
+          if (sparse) {
+            sparse->nz_off[at] = mab_off[ib] + off;
+            sparse->nz_val[at] = x;
+            ++at;
+          } else {
+            base[off] = x;
+          }
         }
       }
     }
   });
+  if (sparse) sparse->perm.swap(perm);
   return "";
+}
+
+const char* host_vbr_fill(int64_t rows_in, int64_t cols_in, const int64_t* rowptr,
+                          const int64_t* colind, const float* val, bool pattern_only,
+                          const int64_t* grouping, int64_t w, int64_t row_block_size,
+                          bool force_fixed, int threads, HostVBR* out) {
+  return vbr_fill_impl(rows_in, cols_in, rowptr, colind, val, pattern_only, grouping, w, row_block_size, force_fixed,
+                       threads, out, nullptr);
+}
+
+const char* host_vbr_fill_sparse(int64_t rows_in, int64_t cols_in, const int64_t* rowptr, const int64_t* colind,
+                                 const float* val, bool pattern_only, const int64_t* grouping, int64_t w,
+                                 int64_t row_block_size, bool force_fixed, int threads, HostVBRSparse* out) {
+  return vbr_fill_impl(rows_in, cols_in, rowptr, colind, val, pattern_only, grouping, w, row_block_size, force_fixed,
+                       threads, &out->index, out);
 }
 
 const char* host_bellpack_from_vbr(int64_t rows, int64_t cols, int64_t bs, const int64_t* nzcount,

@@ -225,6 +225,29 @@ cudaError_t scatter_values(const int64_t* idx_dev, const float* val_dev, int64_t
   return cudaGetLastError();
 }
 
+// The gather rows of a hybrid handle keep their nonzeros in fp32 but ROUNDED to the operand precision,
+// so that both kernel families of a handle compute on the same numbers (pack_a_images rounds the
+// block images the same way).
+__global__ void round_values_kernel(float* __restrict__ val, int64_t n, int precision) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = val[i];
+    float r;
+    if (precision == PREC_TF32) r = __uint_as_float(to_tf32(x));
+    else if (precision == PREC_BF16) r = __bfloat162float(__float2bfloat16_rn(x));
+    else r = __half2float(__float2half_rn(x));
+    val[i] = r;
+  }
+}
+
+cudaError_t round_values(float* val_dev, int64_t n, int precision, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  int64_t grid = (n + 255) / 256;
+  if (grid > stride_grid_cap()) grid = stride_grid_cap();
+  round_values_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(val_dev, n, precision);
+  return cudaGetLastError();
+}
+
 // HBM-bound scatter of C's rows: 2 x rows x n x 4 bytes.  Threads run along whichever dimension is
 // contiguous in the source so the reads coalesce; the writes are 4-byte scatters when C is
 // column-major (consecutive blocked rows map to non-consecutive original rows) and full lines

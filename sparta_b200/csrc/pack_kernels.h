@@ -17,6 +17,9 @@ cudaError_t convert_b(const float* src_dev, int64_t ld_src, int row_major, void*
 cudaError_t scatter_values(const int64_t* idx_dev, const float* val_dev, int64_t nnz, float* dst_dev,
                            cudaStream_t stream);
 
+// val[i] = the value of val[i] rounded to the operand precision (kept as fp32)
+cudaError_t round_values(float* val_dev, int64_t n, int precision, cudaStream_t stream);
+
 // dst[row_map[r]] = src row r for r < rows: C back in the ORIGINAL row order (row_map = the
 // reference's get_permutation, utilities.cpp:8-20).  Both matrices have n columns and arbitrary
 // element strides (row stride sr, column stride sj).

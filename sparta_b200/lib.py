@@ -30,7 +30,7 @@ class Options(C.Structure):
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
         ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
         ("max_chain", C.c_int32), ("split_k", C.c_int32), ("fuse_rows", C.c_int32),
-        ("explicit_range", C.c_int32), ("pipeline", C.c_int32), ("copy_warps", C.c_int32), ("reserved2", C.c_int32 * 3),
+        ("explicit_range", C.c_int32), ("pipeline", C.c_int32), ("copy_warps", C.c_int32), ("gather_max_height", C.c_int32), ("gather_passes", C.c_int32), ("reserved2", C.c_int32 * 1),
     ]
 
 
@@ -43,7 +43,7 @@ class Stats(C.Structure):
         ("grid", C.c_int32), ("smem_bytes", C.c_int32), ("sched_imbalance", C.c_double),
         ("upload_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("team", C.c_int32), ("cta_pair", C.c_int32), ("split_pieces", C.c_int32), ("zero_tiles", C.c_int32),
-        ("sched_max_cycles", C.c_double),
+        ("sched_max_cycles", C.c_double), ("gather_rows", C.c_int64), ("gather_nnz", C.c_int64),
     ]
 
     def as_dict(self):
@@ -61,6 +61,10 @@ SIGNATURES = {
     "sparta_device_count": (C.c_int, []),
     "sparta_vbr_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                     _vp, _vp, _vp, _vp, C.POINTER(Options)]),
+    "sparta_vbr_create_from_csr": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64,
+                                             C.c_int64, C.c_int32, C.POINTER(Options), _vp]),
+    "sparta_csr_vbr_spmm": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int32,
+                                      _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "sparta_vbr_create_BA": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                        _vp, _vp, _vp, _vp, C.POINTER(Options)]),
     "sparta_bellpack_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
@@ -236,6 +240,25 @@ class Handle:
                                      _ptr(row_part), _ptr(nzcount), _ptr(jab), _ptr(mab),
                                      C.byref(o)))
         return cls(h, None)
+
+    @classmethod
+    def from_csr_grouping(cls, rows, cols, rowptr, colind, val, grouping, block_col_size, row_block_size=0,
+                          force_fixed_size=False, **opts):
+        """A from the flat CSR and the row grouping (sparta_vbr_create_from_csr): the dense blocks are
+        rebuilt on the device.  Returns the handle; handle.vbr_dims = rows, cols, block_rows, block_cols,
+        block_col_size, nztot of the VBR."""
+        lib = load()
+        rowptr, colind, grouping = _i64(rowptr), _i64(colind), _i64(grouping)
+        val = None if val is None else _f32(val)
+        o = make_options(**opts)
+        h = _vp()
+        dims = np.zeros(6, dtype=np.int64)
+        _check(lib.sparta_vbr_create_from_csr(C.byref(h), rows, cols, _ptr(rowptr), _ptr(colind),
+                                              None if val is None else _ptr(val), _ptr(grouping), block_col_size,
+                                              row_block_size, int(force_fixed_size), C.byref(o), _ptr(dims)))
+        obj = cls(h, None)
+        obj.vbr_dims = dims
+        return obj
 
     @classmethod
     def from_vbr_BA(cls, rows, cols, block_col_size, row_part, nzcount, jab, mab, **opts):

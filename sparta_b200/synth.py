@@ -93,3 +93,19 @@ def seeded_B(k_rows, n_cols, seed):
     Returned as [n_cols, k_rows] so that row j is column j of the column-major B."""
     rng = np.random.default_rng(seed)
     return rng.random((n_cols, k_rows), dtype=np.float32)
+
+
+def round_to(x, precision):
+    """fp32 values rounded to the operand precision of the tensor-core path (bf16 / fp16: round to
+    nearest even; tf32: cvt.rna.tf32.f32, round to nearest with ties away on the low 13 bits)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if precision == "fp16":
+        return x.astype(np.float16).astype(np.float32)
+    bits = x.view(np.uint32).astype(np.uint64)
+    if precision == "bf16":
+        bits = (bits + 0x7FFF + ((bits >> 16) & 1)) & 0xFFFF0000
+    elif precision == "tf32":
+        bits = (bits + 0x1000) & 0xFFFFE000
+    else:
+        raise ValueError(precision)
+    return bits.astype(np.uint32).view(np.float32)

@@ -34,7 +34,8 @@ def gpu_multiply(v, Bm, n, precision="bf16", **opts):
         h.run()
         out = np.zeros((n, v["rows"]), dtype=np.float32)
         h.get_C(out, v["rows"])
-        assert h.stats()["kernel_launches"] == (1 if len(v["jab"]) else 0)   # no blocks, no work items
+        st = h.stats()   # one launch of the tensor-core kernel if it has work items, one of the gather kernel if it has rows
+        assert st["kernel_launches"] == (1 if st["items"] else 0) + (1 if st["gather_nnz"] else 0)
         return out
     finally:
         h.close()
@@ -368,6 +369,73 @@ def test_split_real_operands_within_tolerance(oracle, lib):
         assert rel_err(Cg, oracle.vbr_multiply(v, Bm, n)) <= TOL_UNROUNDED[precision]
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
+@pytest.mark.parametrize("layout", ["col", "row"])
+def test_short_block_rows_on_the_gather_kernel(oracle, lib, precision, layout):
+    """Block-rows of at most gather_max_height rows (default 7) leave the tile schedule and run, as
+    the nonzeros of their blocks, on the gather kernel of the family; the rest stays on the tensor
+    cores.  Same product: integer operands bit-exact with gathering on, off and at another
+    threshold; real operands within the stated tolerances; accumulate = 1; both C layouts."""
+    rng = np.random.default_rng(77)
+    heights = [1, 1, 64, 3, 1, 7, 8, 1, 1, 30, 2, 1, 1, 1, 5, 64, 1, 4, 1, 6, 1, 1, 16, 1] * 3
+    v = random_vbr(rng, len(heights), 1000, 64, heights, 0.35, values="int")     # cols % w != 0
+    # make the short blocks sparse inside, like the blocks of a clustered sparse matrix
+    keep = rng.random(v["mab"].shape) < 0.1
+    v["mab"] = (v["mab"] * keep).astype(np.float32)
+    n = 200
+    Bm = rng.integers(-3, 4, size=(n, 1000)).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    lay = dict(b_layout=2, c_layout=2) if layout == "row" else {}
+
+    def run(values_v, B, accumulate=0, C0=None, **opts):
+        h = sparta_b200.Handle.from_vbr(v["rows"], 1000, 64, values_v["row_part"], values_v["nzcount"], values_v["jab"],
+                                        values_v["mab"], precision=precision, accumulate=accumulate, **lay, **opts)
+        try:
+            if layout == "row":
+                h.set_B(np.ascontiguousarray(B.T), n, n)
+            else:
+                h.set_B(B, 1000, n)
+            if C0 is not None:
+                h.set_C(np.ascontiguousarray(C0.T) if layout == "row" else C0, n if layout == "row" else v["rows"])
+            h.run()
+            st = h.stats()
+            if layout == "row":
+                out = h.get_C(np.zeros((v["rows"], n), np.float32), n).T.copy()
+            else:
+                out = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"])
+            return out, st
+        finally:
+            h.close()
+
+    on, st_on = run(v, Bm)
+    off, st_off = run(v, Bm, gather_max_height=-1)
+    upto16, st16 = run(v, Bm, gather_max_height=16)
+    # the gather rows walked in 5 ranges of k (one launch each; pass 0 writes, the others add)
+    passes5, st5 = run(v, Bm, gather_passes=5)
+    assert np.array_equal(passes5, Cref) and st5["kernel_launches"] == 1 + 5
+    hs = np.asarray(heights)
+    assert st_on["gather_rows"] == int(hs[hs <= 7].sum()) and st_off["gather_rows"] == 0
+    assert st16["gather_rows"] == int(hs[hs <= 16].sum())
+    assert st_on["gather_nnz"] > 0 and st_on["nztot"] == st_off["nztot"] == v["mab"].size
+    assert st_on["nz_blocks"] == st_off["nz_blocks"] == len(v["jab"])
+    assert st_on["chunks"] < st_off["chunks"]          # the short block-rows left the tile schedule
+    for out in (on, off, upto16):
+        assert np.array_equal(out, Cref)
+    # beta = 1
+    C0 = rng.integers(-5, 6, size=(n, v["rows"])).astype(np.float32)
+    acc, _ = run(v, Bm, accumulate=1, C0=C0)
+    assert np.array_equal(acc, Cref + C0)
+    # real values: both kernel families round their operands to the handle's precision
+    vr = dict(v)
+    # same sparsity as the integer matrix (its mask also zeroes the columns past the matrix edge in the
+    # last column block, as the reference's fill does, vbr.cpp:205-227)
+    vr["mab"] = (rng.uniform(-1, 1, size=v["mab"].shape) * (v["mab"] != 0)).astype(np.float32)
+    Br = rng.uniform(0, 1, size=(n, 1000)).astype(np.float32)
+    got, _ = run(vr, Br)
+    assert rel_err(got, oracle.vbr_multiply(rounded(vr, precision), round_to(Br, precision), n)) <= TOL_ROUNDED
+    assert rel_err(got, oracle.vbr_multiply(vr, Br, n)) <= TOL_UNROUNDED[precision]
+
+
 BA_CASES = [
     (6, 96, 16, [16] * 6, 0.5, 40),
     (5, 70, 16, [3, 17, 1, 64, 30], 0.6, 130),      # ragged heights = ragged k extents; cols % w != 0
@@ -585,3 +653,85 @@ def test_shards_scatter_into_one_matrix_in_original_order(oracle, lib):
         h.close()
     torch.cuda.synchronize()
     assert np.array_equal(full.cpu().numpy(), Cref)
+
+
+@pytest.mark.parametrize("flags", [dict(a=5, b=16, B=16, t=0.6), dict(a=4, b=8, B=8, t=0.5), dict(a=3, b=16, B=16, t=0.4, F=1),
+                                   dict(a=2, b=64, B=64, F=1)],
+                         ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()))
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_handle_from_csr_and_grouping(oracle, lib, flags, precision):
+    """sparta_vbr_create_from_csr: A from the flat CSR + the row grouping, dense blocks rebuilt on the
+    device (the fp32 mab never exists on the host).  Against (i) the handle built from the VBR arrays
+    of sparta_host_vbr_fill -- same C bit for bit, same nztot / block counts -- and (ii) the oracle's
+    VBR::multiply; weighted values, -F 1 padding, variable heights (gather rows), shards."""
+    from sparta_b200 import lib as L
+    rng = np.random.default_rng(5)
+    r, c = synth.rmat_edges(10, 9000, seed=4)
+    keep = c < 1000
+    r, c = synth.pin_shape(r[keep], c[keep], 1024, 1000)
+    vals = rng.integers(-3, 4, size=len(r)).astype(np.float32)
+    vals[vals == 0] = 1
+    rowptr, colind, val = synth.csr_from_edges(r, c, 1024, vals)
+    f = dict(a=3, b=3, B=3, t=0.1, F=0)
+    f.update(flags)
+    g = L.host_blocking(1024, 1000, rowptr, colind, algo=f["a"], tau=f["t"], block_col_size=f["b"],
+                        row_block_size=f["B"], sim_measure=1, use_pattern=True, force_fixed_size=bool(f["F"]))
+    v = L.host_vbr_fill(1024, 1000, rowptr, colind, val, g, f["b"], f["B"], bool(f["F"]))
+    n = 96
+    Bm = rng.integers(-3, 4, size=(n, v["cols"])).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+
+    def product(h, rows):
+        try:
+            h.set_B(Bm, v["cols"], n)
+            h.run()
+            return h.get_C(np.zeros((n, rows), np.float32), rows), h.stats()
+        finally:
+            h.close()
+
+    a, st_a = product(sparta_b200.Handle.from_vbr(v["rows"], v["cols"], f["b"], v["row_part"], v["nzcount"], v["jab"],
+                                                  v["mab"], precision=precision), v["rows"])
+    hc = sparta_b200.Handle.from_csr_grouping(1024, 1000, rowptr, colind, val, g, f["b"], f["B"], bool(f["F"]),
+                                              precision=precision)
+    assert hc.vbr_dims.tolist() == [v["rows"], v["cols"], v["block_rows"], v["block_cols"], f["b"], v["nztot"]]
+    b, st_b = product(hc, v["rows"])
+    assert np.array_equal(a, Cref) and np.array_equal(b, Cref)
+    for k in ("rows", "block_rows", "nz_blocks", "nztot", "chunks", "items", "gather_rows", "gather_nnz"):
+        assert st_a[k] == st_b[k], k
+    # pattern-only (val = NULL) and two shards
+    vp = L.host_vbr_fill(1024, 1000, rowptr, colind, None, g, f["b"], f["B"], bool(f["F"]), pattern_only=True)
+    Cp = oracle.vbr_multiply(vp, Bm, n)
+    cut = v["block_rows"] // 2
+    parts = []
+    for lo, hi in ((0, cut), (cut, v["block_rows"])):
+        rows_s = int(v["row_part"][hi] - v["row_part"][lo])
+        hs = sparta_b200.Handle.from_csr_grouping(1024, 1000, rowptr, colind, None, g, f["b"], f["B"], bool(f["F"]),
+                                                  precision=precision, block_row_begin=lo, block_row_end=hi)
+        if rows_s == 0:
+            hs.close()
+            continue
+        parts.append(product(hs, rows_s)[0])
+    assert np.array_equal(np.concatenate(parts, axis=1), Cp)
+
+
+def test_one_shot_from_csr(oracle, lib):
+    """sparta_csr_vbr_spmm: host CSR + grouping + B in, host C out, real values within tolerance."""
+    import ctypes as C
+    from sparta_b200 import lib as L
+    rng = np.random.default_rng(6)
+    r, c = synth.rmat_edges(10, 12000, seed=8)
+    r, c = synth.pin_shape(r, c, 1024, 1024)
+    rowptr, colind, val = synth.csr_from_edges(r, c, 1024, rng.uniform(-1, 1, size=len(r)))
+    g = L.host_blocking(1024, 1024, rowptr, colind, algo=5, tau=0.6, block_col_size=32, row_block_size=32, sim_measure=1,
+                        use_pattern=True)
+    v = L.host_vbr_fill(1024, 1024, rowptr, colind, val, g, 32, 32, False)
+    n = 130
+    Bm = rng.uniform(0, 1, size=(n, 1024)).astype(np.float32)
+    out = np.zeros((n, 1024), np.float32)
+    dt = C.c_float(0)
+    g64 = np.ascontiguousarray(g, dtype=np.int64)
+    L._check(lib.sparta_csr_vbr_spmm(1024, 1024, L._ptr(rowptr), L._ptr(colind), L._ptr(val), L._ptr(g64), 32, 32, 0,
+                                     L._ptr(Bm), 1024, n, L._ptr(out), 1024, L.PRECISIONS["bf16"], C.byref(dt)))
+    assert dt.value > 0
+    assert rel_err(out, oracle.vbr_multiply(rounded(v, "bf16"), round_to(Bm, "bf16"), n)) <= TOL_ROUNDED
+    assert rel_err(out, oracle.vbr_multiply(v, Bm, n)) <= TOL_UNROUNDED["bf16"]
