@@ -480,8 +480,11 @@ def run_ours(args, wl):
         if rows_shard:
             c_resident = np.zeros((n, rows_shard), dtype=np.float32)
             h.get_C(c_resident, rows_shard)
+        val_csr = None
+        if args.weighted:
+            val_csr = np.random.default_rng(3).uniform(-1.0, 1.0, size=len(colind)).astype(np.float32)
         e2e = run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist if world > 1 else None, total_flops,
-                      c_resident)
+                      c_resident, (N, rowptr, colind, val_csr), grouping)
     h.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
@@ -660,75 +663,133 @@ def gather_c(h, v, cuts, n, rank, world, dev, dist):
             "how": "slabs padded to the tallest, one NCCL all_gather, padding cut away (sparta_b200/dist.py)"}
 
 
-def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_resident=None):
-    """One-shot sparta_vbr_spmm on this rank's shard: host arrays in, host C out.  The C it returns
-    is compared with the resident handle's (which spot_check verified against fp64)."""
+def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_resident, csr, grouping):
+    """End to end through the public API with HOST buffers, every copy inside the timed region.
+
+    N = 1: the one-shot sparta_csr_vbr_spmm -- host CSR + grouping + host B in, host C out.  It
+    replaces fill_from_CSR_inplace + cublas_fixed_blocks_multiply (cuda_multiply.cpp:129-137): index
+    arrays on the host, dense blocks rebuilt on the device from the nonzeros, kernel, download.
+    N > 1: the same flow sharded -- every rank builds the handle of ITS block-rows from the CSR
+    (Handle.from_csr_grouping), rank 0 alone uploads B and ONE NCCL broadcast replicates it, every rank
+    multiplies and downloads its slab of C.  `vbr_arrays` times the drop-in sparta_vbr_spmm call (host
+    VBR arrays incl. the fp32 mab in) on the rank's shard beside it."""
     import ctypes as C
     import torch
     import sparta_b200
     from sparta_b200 import lib as L
     lib = sparta_b200.load()
     rp, nz, w = v["row_part"], v["nzcount"], v["block_col_size"]
-    if dist is not None:
-        Bt = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
-        if rank == 0:
-            Bt.copy_(torch.from_numpy(Bm))
-        dist.broadcast(Bt, 0)
-        Bm = Bt.cpu().numpy()
-        del Bt
-    jab_off = np.concatenate([[0], np.cumsum(nz)])
-    mab_off = np.concatenate([[0], np.cumsum(nz * np.diff(rp) * w)])
+    N_rows, rowptr, colind, val = csr
     rows_s = int(rp[hi] - rp[lo])
-    # pinned host buffers, as the contract asks
+
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
-    k_rp, a_rp = pin((rp[lo:hi + 1] - rp[lo]).astype(np.int64))
-    k_nz, a_nz = pin(nz[lo:hi].astype(np.int64))
-    k_jab, a_jab = pin(v["jab"][jab_off[lo]:jab_off[hi]].astype(np.int64))
-    k_mab, a_mab = pin(v["mab"][mab_off[lo]:mab_off[hi]])
-    k_B, a_B = pin(Bm)
+    k_rowptr, a_rowptr = pin(rowptr.astype(np.int64))
+    k_colind, a_colind = pin(colind.astype(np.int64))
+    k_grp, a_grp = pin(np.asarray(grouping, dtype=np.int64))
+    a_val = None
+    if val is not None:
+        k_val, a_val = pin(val.astype(np.float32))
     k_C = torch.zeros((n, max(rows_s, 1)), dtype=torch.float32).pin_memory()
     a_C = k_C.numpy()
-    h2d = a_rp.nbytes + a_nz.nbytes + a_jab.nbytes + a_mab.nbytes + a_B.nbytes
-    d2h = rows_s * n * 4
+    if rank == 0:
+        k_B, a_B = pin(Bm)
     steps = max(1, min(args.steps, args.e2e_steps))
     dt = C.c_float(0)
+    fixed = wl["algo"] == 2
+    Bd = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev) if world > 1 else None
+    stream = None
 
     def once():
-        L._check(lib.sparta_vbr_spmm(rows_s, v["cols"], hi - lo, w, L._ptr(a_rp), L._ptr(a_nz), L._ptr(a_jab),
-                                     L._ptr(a_mab), L._ptr(a_B), v["cols"], n, L._ptr(a_C), max(rows_s, 1),
-                                     L.PRECISIONS[args.precision], C.byref(dt)))
-    if rows_s:
-        once()  # warm-up (context, allocator)
+        if world == 1:
+            L._check(lib.sparta_csr_vbr_spmm(N_rows, N_rows, L._ptr(a_rowptr), L._ptr(a_colind),
+                                             None if a_val is None else L._ptr(a_val), L._ptr(a_grp), w, wl["rb"],
+                                             int(fixed), L._ptr(a_B), v["cols"], n, L._ptr(a_C), max(rows_s, 1),
+                                             L.PRECISIONS[args.precision], C.byref(dt)))
+            return
+        hh = sparta_b200.Handle.from_csr_grouping(N_rows, N_rows, a_rowptr, a_colind, a_val, a_grp, w, wl["rb"], fixed,
+                                                  precision=args.precision, device=dev.index, block_row_begin=lo,
+                                                  block_row_end=hi, **tuning_opts(args))
+        try:
+            if rank == 0:
+                Bd.copy_(k_B, non_blocking=True)          # the ONE upload of B
+            dist.broadcast(Bd, 0)                          # NCCL over NVLink
+            torch.cuda.current_stream().synchronize()
+            if rows_s:
+                hh.set_B_device(Bd.data_ptr(), v["cols"], n)
+                hh.run()
+                hh.get_C(a_C[:, :rows_s] if a_C.shape[1] == rows_s else a_C, max(rows_s, 1))
+        finally:
+            hh.close()
+
+    once()  # warm-up (context, allocator, NCCL channel)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        if rows_s:
-            once()
+        once()
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     sec = time.perf_counter() - t0
     diff = 0.0
     if rows_s and c_resident is not None:
         scale = float(np.abs(c_resident).max()) or 1.0
         diff = float(np.abs(a_C[:, :rows_s] - c_resident).max()) / scale
-    t_all = torch.tensor([sec, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    h2d = a_rowptr.nbytes + a_colind.nbytes + a_grp.nbytes + (a_val.nbytes if a_val is not None else 0)
+    h2d_b = Bm.nbytes if rank == 0 else 0
+    d2h = rows_s * n * 4
+    t_all = torch.tensor([sec, float(h2d_b), float(d2h), float(diff)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t_all.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dmax = torch.tensor([diff], dtype=torch.float64, device=dev)
-        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
-        diff = float(dmax.item())
         dist.all_reduce(t_all, op=dist.ReduceOp.SUM)
-        sec = float(tmax[0].item())
-        h2d, d2h = float(t_all[1].item()), float(t_all[2].item())
-    return {"value": total_flops * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * sec / steps,
-            "max_rel_diff_vs_resident_handle": diff, "same_result": bool(diff <= 1e-6),
-            "call": "sparta_vbr_spmm (host VBR + host B -> host C; upload, repack, kernel, download per call; "
-                    "pinned host buffers; wall clock, max over ranks)"}
+        sec, diff = float(tmax[0].item()), float(tmax[3].item())
+        h2d_b, d2h = float(t_all[1].item()), float(t_all[2].item())
+    # nonzeros actually sent: this rank's (offset, value) pairs; the index arrays are host-side input
+    out = {"value": total_flops * steps / sec / 1e12, "unit": "TFLOP/s",
+           "h2d_bytes_per_step": int(h2d_b + len(colind) * 12 + 0), "d2h_bytes_per_step": int(d2h), "steps": steps,
+           "ms_per_step": 1e3 * sec / steps, "max_rel_diff_vs_resident_handle": diff,
+           "same_result": bool(diff <= 1e-6), "host_input_bytes": int(h2d + Bm.nbytes if rank == 0 else h2d),
+           "call": ("sparta_csr_vbr_spmm (host CSR + grouping + host B -> host C: index build, nonzeros and B up, "
+                    "device-side block rebuild + pack, kernel, C down; pinned host buffers; wall clock)" if world == 1 else
+                    "per rank Handle.from_csr_grouping on its block-rows + B uploaded by rank 0 and ONE NCCL broadcast + "
+                    "run + download of the rank's C slab; wall clock, max over ranks"),
+           "h2d_note": "B (fp32) + 12 bytes per nonzero (element offset + value); the host-side index build is inside the timed region"}
+    # the drop-in call on host VBR arrays (fp32 mab included), this rank's shard, one repetition
+    jab_off = np.concatenate([[0], np.cumsum(nz)])
+    mab_off = np.concatenate([[0], np.cumsum(nz * np.diff(rp) * w)])
+    if rows_s and not args.no_e2e_vbr:
+        if dist is not None:
+            Bt = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
+            if rank == 0:
+                Bt.copy_(torch.from_numpy(Bm))
+            dist.broadcast(Bt, 0)
+            Bm = Bt.cpu().numpy()
+            del Bt
+        k1, a_rp = pin((rp[lo:hi + 1] - rp[lo]).astype(np.int64))
+        k2, a_nz = pin(nz[lo:hi].astype(np.int64))
+        k3, a_jab = pin(v["jab"][jab_off[lo]:jab_off[hi]].astype(np.int64))
+        k4, a_mab = pin(v["mab"][mab_off[lo]:mab_off[hi]])
+        k5, a_B2 = pin(Bm)
+
+        def once_vbr():
+            L._check(lib.sparta_vbr_spmm(rows_s, v["cols"], hi - lo, w, L._ptr(a_rp), L._ptr(a_nz), L._ptr(a_jab),
+                                         L._ptr(a_mab), L._ptr(a_B2), v["cols"], n, L._ptr(a_C), max(rows_s, 1),
+                                         L.PRECISIONS[args.precision], C.byref(dt)))
+        once_vbr()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        once_vbr()
+        torch.cuda.synchronize()
+        sec_v = time.perf_counter() - t0
+        d2 = float(np.abs(a_C[:, :rows_s] - c_resident).max()) / (float(np.abs(c_resident).max()) or 1.0) if c_resident is not None else 0.0
+        out["vbr_arrays"] = {"ms_per_step_this_rank": 1e3 * sec_v, "h2d_bytes": int(a_rp.nbytes + a_nz.nbytes + a_jab.nbytes + a_mab.nbytes + a_B2.nbytes),
+                             "max_rel_diff_vs_resident_handle": d2,
+                             "call": "sparta_vbr_spmm on the rank's shard (host VBR arrays incl. the fp32 mab + host B -> host C)"}
+    return out
 
 
 def main():
@@ -743,6 +804,7 @@ def main():
     ap.add_argument("--weighted", action="store_true", help="uniform(-1,1) values instead of the pattern-only matrix")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e-vbr", action="store_true", help="skip the extra timing of the sparta_vbr_spmm call on host VBR arrays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-c", action="store_true", help="multi-GPU: also all-gather C over NCCL and verify it")
     ap.add_argument("--cpu-gflop", type=float, default=40.0, help="size of the cpu_baseline sample")

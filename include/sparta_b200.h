@@ -86,9 +86,9 @@ typedef struct sparta_options {
                             family (csr_kernel.cu) on the NONZEROS of their blocks -- same numbers, operands rounded
                             to the handle's precision, fp32 accumulation.  0: default (7), -1: off, k > 0: heights <= k.
                             Variable-height blockings (-a 3 / -a 4) leave most block-rows one row tall. */
-  int32_t gather_passes;  /* launches of the gather kernel per multiply, each over one range of A's columns, so that
-                            the rows of B a launch reads stay L2-resident.  0: as many as keep (columns per pass)
-                            x 256 x element size within 48 MB (default; 1 up to 2^16 columns in fp32), k > 0: k */
+  int32_t gather_passes;  /* launches of the gather kernel per multiply, each over one range of A's columns (the rows
+                            of B a launch reads are a smaller slab).  0/1: one (default: measured faster than 6 or 8
+                            passes even at 2^18 columns, where a tile's slab of B is 268 MB), k > 1: k */
   int32_t reserved2[1];
 } sparta_options;
 
@@ -242,6 +242,19 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
                     const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
                     const float* mab, const float* B, int64_t ldb, int64_t n, float* C,
                     int64_t ldc, int precision, float* dt_ms);
+
+/* sparta_vbr_spmm on the first n_gpus sm_100 devices of the box (one process): A sharded by contiguous
+ * block-row ranges balanced on modelled shard time, B uploaded ONCE and replicated by a single
+ * ncclBroadcast over NVLink, no exchange during the multiply, C row-partitioned -- every device
+ * copies its slab into the caller's C; gather_c != 0 all-gathers the slabs over NCCL first and
+ * returns the whole C from device 0.  *dt_ms = the slowest device's kernel time, *bcast_ms (may be
+ * NULL) = upload + broadcast of B.  NCCL is loaded at run time (libnccl.so.2); without it the call
+ * fails with SPARTA_ERR_STATE.  The reference has no counterpart (SURVEY.md section 5, 8b "n_gpus,
+ * gather_c"); integration/cuda_utilities_b200.cpp routes -M 4 / -M 7 here when SPARTA_GPUS > 1. */
+int sparta_vbr_spmm_multi(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                          const int64_t* row_part, const int64_t* nzcount, const int64_t* jab,
+                          const float* mab, const float* B, int64_t ldb, int64_t n, float* C, int64_t ldc,
+                          int precision, int32_t n_gpus, int32_t gather_c, float* dt_ms, float* bcast_ms);
 
 /* The same one-shot flow from the CSR and the grouping (sparta_vbr_create_from_csr): what
  * fill_from_CSR_inplace + cublas_fixed_blocks_multiply do together in cuda_multiply.cpp:129-137.

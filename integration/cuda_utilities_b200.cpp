@@ -114,9 +114,21 @@ double vbr_nztot(const VBR& A, long* blocks) {
 void vbr_multiply(const VBR& A, DataT* B, int B_cols, DataT_C* C, float& dt, int precision) {
   static_assert(sizeof(intT) == sizeof(int64_t) && sizeof(DataT) == sizeof(float) && sizeof(DataT_C) == sizeof(float),
                 "the C ABI takes the reference's default types (definitions.h:4-6)");
-  if (sparta_vbr_spmm(A.rows, A.cols, A.block_rows, A.block_col_size,
-                      reinterpret_cast<const int64_t*>(A.row_part), reinterpret_cast<const int64_t*>(A.nzcount),
-                      reinterpret_cast<const int64_t*>(A.jab), A.mab, B, A.cols, B_cols, C, A.rows, precision, &dt))
+  // SPARTA_GPUS=k (k > 1): the same call on k GPUs of the box -- A sharded by block-rows, B replicated
+  // by one NCCL broadcast, C row-partitioned (SPARTA_GATHER_C=1: all-gathered over NCCL first)
+  const char* g = getenv("SPARTA_GPUS");
+  const int gpus = g ? atoi(g) : 1;
+  if (gpus > 1) {
+    const char* gc = getenv("SPARTA_GATHER_C");
+    float bcast_ms = 0;
+    if (sparta_vbr_spmm_multi(A.rows, A.cols, A.block_rows, A.block_col_size,
+                              reinterpret_cast<const int64_t*>(A.row_part), reinterpret_cast<const int64_t*>(A.nzcount),
+                              reinterpret_cast<const int64_t*>(A.jab), A.mab, B, A.cols, B_cols, C, A.rows, precision,
+                              gpus, gc && atoi(gc), &dt, &bcast_ms))
+      die("sparta_vbr_spmm_multi");
+  } else if (sparta_vbr_spmm(A.rows, A.cols, A.block_rows, A.block_col_size,
+                             reinterpret_cast<const int64_t*>(A.row_part), reinterpret_cast<const int64_t*>(A.nzcount),
+                             reinterpret_cast<const int64_t*>(A.jab), A.mab, B, A.cols, B_cols, C, A.rows, precision, &dt))
     die("sparta_vbr_spmm");
   long nb = 0;
   const double nztot = vbr_nztot(A, &nb);

@@ -6,10 +6,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsparta_b200.so")
-SOURCES = ["abi.cu", "spmm_kernel.cu", "csr_kernel.cu", "pack_kernels.cu", "schedule.cpp", "host_formats.cpp", "blocking.cpp"]
+SOURCES = ["abi.cu", "spmm_kernel.cu", "csr_kernel.cu", "pack_kernels.cu", "multi_gpu.cu", "schedule.cpp", "host_formats.cpp", "blocking.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--shared", "-cudart", "static", "-Xcompiler", "-pthread",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--shared", "-cudart", "static", "-Xcompiler", "-pthread", "-ldl",
 ]
 
 

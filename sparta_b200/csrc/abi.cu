@@ -37,6 +37,8 @@ static int fail_cuda(cudaError_t e, const char* what) {
   g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
   return SPARTA_ERR_CUDA;
 }
+// for the other translation units of the library (multi_gpu.cu)
+int sparta_internal_fail(int code, const std::string& msg) { return fail(code, msg); }
 #define CU_TRY(call)                                        \
   do {                                                      \
     cudaError_t e_ = (call);                                \
@@ -362,8 +364,12 @@ static void build_gather_passes(GatherPart* g, const std::vector<int32_t>& live,
                                 int esize_b, int force_passes) {
   // a pass's slab of B (range x 256 columns) within ~48 MB
   const double slab = static_cast<double>(cols) * 256.0 * esize_b;
-  const int P = force_passes > 0 ? std::min(force_passes, 64)
-                                 : static_cast<int>(std::max(1.0, std::min(16.0, std::ceil(slab / 48e6))));
+  // Measured at BASELINE config #4 (2^18 columns, fp32 rows of B, 70 nonzeros per gather row): 1 pass
+  // 38.0 ms, 6 passes 102.9, 8 passes 126.1 -- the rows' segments get too short to amortise a warp's
+  // fixed work and every pass after the first read-modify-writes its rows of C, so one pass is the default
+  // although a column tile's slab of B (268 MB there) no longer fits the L2.
+  (void)slab;
+  const int P = force_passes > 0 ? std::min(force_passes, 64) : 1;
   const int64_t range = ((cols + P - 1) / P + 63) / 64 * 64;
   g->passes.assign(P, GatherPart::Pass());
   for (int pi = 0; pi < P; ++pi) {

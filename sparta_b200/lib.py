@@ -87,6 +87,9 @@ SIGNATURES = {
     "sparta_vbr_spmm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
                                   _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
                                   C.POINTER(C.c_float)]),
+    "sparta_vbr_spmm_multi": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
+                                        _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "sparta_vbr_spmm_BA": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
                                      _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int,
                                      C.POINTER(C.c_float)]),
