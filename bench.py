@@ -394,13 +394,20 @@ def run_ours(args, wl):
     v = build_vbr(wl, N, rowptr, colind, grouping, args.weighted)
     t_fill = time.perf_counter() - t0
     n = wl["n"]
-    if args.partition == "model":
-        # contiguous block-row ranges balanced on the scheduler's modelled kernel time per shard
-        cuts = sparta_b200.partition_block_rows_modelled(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"],
-                                                         v["jab"], n, world, precision=args.precision,
-                                                         **tuning_opts(args))
-    else:
-        cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
+    if rank == 0:
+        if args.partition == "model":
+            # contiguous block-row ranges balanced on the scheduler's modelled kernel time per shard
+            cuts = sparta_b200.partition_block_rows_modelled(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"],
+                                                             v["jab"], n, world, precision=args.precision,
+                                                             **tuning_opts(args))
+        else:
+            cuts = sparta_b200.partition_block_rows(v["row_part"], v["nzcount"], world)
+    if world > 1:   # one rank cuts (a few seconds of host threads at 10^5 block-rows), everybody gets the cuts
+        ct = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            ct.copy_(torch.from_numpy(np.asarray(cuts, dtype=np.int64)))
+        dist.broadcast(ct, 0)
+        cuts = ct.cpu().numpy()
     lo, hi = int(cuts[rank]), int(cuts[rank + 1])
     if rank == 0:
         log(f"[bench] matrix {N}x{N} nnz={len(colind)} gen {t_gen:.1f}s blocking {t_block:.1f}s fill {t_fill:.1f}s "
@@ -459,7 +466,11 @@ def run_ours(args, wl):
     clocks = sampler.stop(tm0, tm1) if rank == 0 else None
     launches = h.stats()["kernel_launches"] - launches_before
     t_all = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms / args.steps]
     if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, t_all)
+        per_rank_ms = [float(g.item()) / args.steps for g in gathered]
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms_max = float(t_all.item())
     value = total_flops * args.steps / (ms_max * 1e-3) / 1e12
@@ -544,7 +555,7 @@ def run_ours(args, wl):
                       "sched_imbalance": st["sched_imbalance"], "grid": st["grid"], "items": st["items"],
                       "team": st["team"], "split_pieces": st["split_pieces"], "zero_tiles": st["zero_tiles"],
                       "gather_rows": st["gather_rows"], "gather_nnz": st["gather_nnz"], "chunks": st["chunks"],
-                      "shard_block_rows": [int(c) for c in cuts]},
+                      "shard_block_rows": [int(c) for c in cuts], "per_rank_ms_per_step": per_rank_ms},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -723,7 +734,8 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_r
         finally:
             hh.close()
 
-    once()  # warm-up (context, allocator, NCCL channel)
+    for _ in range(2):   # warm-up (context, stream-ordered allocator pools of two streams, NCCL channel)
+        once()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -53,6 +54,28 @@ static void parallel_for(int64_t n, int threads, F fn) {
   for (auto& th : pool) th.join();
 }
 
+// fn(lo, hi) over [0, n) cut into one range per thread of about equal WEIGHT (prefix[i] = weight of the
+// items before i): the block-rows of a clustered matrix are sorted dense first, equal counts are not equal work.
+template <class F>
+static void parallel_for_weighted(int64_t n, int threads, const std::vector<int64_t>& prefix, F fn) {
+  if (threads <= 1 || n < 2) {
+    fn(0, n);
+    return;
+  }
+  threads = static_cast<int>(std::min<int64_t>(threads, n));
+  std::vector<int64_t> cut(threads + 1, 0);
+  for (int t = 1; t < threads; ++t) {
+    const int64_t target = prefix[n] * t / threads;
+    cut[t] = std::max<int64_t>(cut[t - 1], std::lower_bound(prefix.begin(), prefix.begin() + n + 1, target) - prefix.begin());
+    cut[t] = std::min(cut[t], n);
+  }
+  cut[threads] = n;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    if (cut[t] < cut[t + 1]) pool.emplace_back([=] { fn(cut[t], cut[t + 1]); });
+  for (auto& th : pool) th.join();
+}
+
 // dense: the reference's arrays, mab included.  sparse != nullptr: mab is NOT built; the nonzeros go to
 // sparse->nz_* as (offset into the virtual mab, value) and the permutation is kept.
 static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t* rowptr,
@@ -61,15 +84,38 @@ static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t
                                  bool force_fixed, int threads, HostVBR* out, HostVBRSparse* sparse) {
   if (w <= 0) return "column block size must be positive";
   if (force_fixed && row_block_size <= 0) return "force_fixed needs a positive row block size";
-  for (int64_t i = 0; i < rows_in; ++i) {
-    if (rowptr[i + 1] < rowptr[i]) return "rowptr must be non-decreasing";
-    for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p)
-      if (colind[p] < 0 || colind[p] >= cols_in) return "column index out of range";
-  }
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(now() - a).count(); };
+  const auto tp0 = now();
   std::vector<int64_t> perm(rows_in), part(rows_in + 1);
-  host_permutation(grouping, rows_in, perm.data());
-  part.resize(host_partition(grouping, rows_in, part.data()));
+  {
+    // input check (all threads), permutation and partition side by side
+    std::vector<char> bad(static_cast<size_t>(std::max(threads, 1)), 0);
+    std::thread t_perm([&] { host_permutation(grouping, rows_in, perm.data()); });
+    std::thread t_part([&] { part.resize(host_partition(grouping, rows_in, part.data())); });
+    for (int64_t i = 0; i < rows_in; ++i)
+      if (rowptr[i + 1] < rowptr[i]) bad[0] = 1;
+    if (!bad[0]) {
+      const int64_t nnz = rowptr[rows_in] - rowptr[0];
+      const int T = std::max(threads, 1);
+      std::vector<std::thread> pool;
+      for (int t = 0; t < T; ++t)
+        pool.emplace_back([&, t] {
+          const int64_t lo = rowptr[0] + nnz * t / T, hi = rowptr[0] + nnz * (t + 1) / T;
+          char b = 0;
+          for (int64_t p = lo; p < hi; ++p) b |= (colind[p] < 0) | (colind[p] >= cols_in);
+          bad[t] = b ? 2 : 0;
+        });
+      for (auto& th : pool) th.join();
+    }
+    t_perm.join();
+    t_part.join();
+    if (bad[0] == 1) return "rowptr must be non-decreasing";
+    for (char b : bad) if (b) return "column index out of range";
+  }
 
+  const double t_perm = since(tp0);
   int64_t rows = rows_in, cols = cols_in;
   if (force_fixed) {  // vbr.cpp:142-147: pad to whole blocks, the last block-row absorbs the padding rows
     rows = ((rows_in - 1) / row_block_size + 1) * row_block_size;
@@ -83,9 +129,16 @@ static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t
   out->row_part = part;
   out->nzcount.assign(block_rows, 0);
 
+  // nonzeros per block-row: the weight the two passes are balanced on
+  std::vector<int64_t> nnz_prefix(block_rows + 1, 0);
+  for (int64_t ib = 0; ib < block_rows; ++ib) {
+    int64_t cnt = 0;
+    for (int64_t r = part[ib]; r < part[ib + 1] && r < rows_in; ++r) cnt += rowptr[perm[r] + 1] - rowptr[perm[r]];
+    nnz_prefix[ib + 1] = nnz_prefix[ib] + cnt + 1;
+  }
   // pass 1: distinct column blocks per block-row (stamp array per thread)
   std::vector<std::vector<int64_t>> row_jab(block_rows);
-  parallel_for(block_rows, threads, [&](int64_t lo, int64_t hi) {
+  parallel_for_weighted(block_rows, threads, nnz_prefix, [&](int64_t lo, int64_t hi) {
     std::vector<int64_t> stamp(block_cols, -1);
     for (int64_t ib = lo; ib < hi; ++ib) {
       std::vector<int64_t>& list = row_jab[ib];
@@ -102,6 +155,7 @@ static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t
     }
   });
 
+  const double t_pass1 = since(tp0);
   // offsets
   std::vector<int64_t> jab_off(block_rows + 1, 0), mab_off(block_rows + 1, 0);
   for (int64_t ib = 0; ib < block_rows; ++ib) {
@@ -118,14 +172,15 @@ static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t
       for (int64_t r = part[ib]; r < part[ib + 1] && r < rows_in; ++r) cnt += rowptr[perm[r] + 1] - rowptr[perm[r]];
       sparse->nz_ptr[ib + 1] = sparse->nz_ptr[ib] + cnt;
     }
-    sparse->nz_off.resize(static_cast<size_t>(sparse->nz_ptr[block_rows]));
-    sparse->nz_val.resize(static_cast<size_t>(sparse->nz_ptr[block_rows]));
+    if (!sparse->nz_off.alloc(static_cast<size_t>(sparse->nz_ptr[block_rows])) ||
+        !sparse->nz_val.alloc(static_cast<size_t>(sparse->nz_ptr[block_rows])))
+      return "out of memory";
   } else {
     out->mab.assign(static_cast<size_t>(out->nztot), 0.0f);
   }
 
   // pass 2: scatter values; block (ib, slot) is column-major with ld = h (vbr.cpp:224)
-  parallel_for(block_rows, threads, [&](int64_t lo, int64_t hi) {
+  parallel_for_weighted(block_rows, threads, nnz_prefix, [&](int64_t lo, int64_t hi) {
     std::vector<int64_t> slot(block_cols, 0);
     for (int64_t ib = lo; ib < hi; ++ib) {
       const std::vector<int64_t>& list = row_jab[ib];
@@ -153,6 +208,9 @@ static const char* vbr_fill_impl(int64_t rows_in, int64_t cols_in, const int64_t
     }
   });
   if (sparse) sparse->perm.swap(perm);
+  if (timing)
+    fprintf(stderr, "sparta vbr fill (%s, %d threads): validate + permutation %.1f ms, column-block lists %.1f, values %.1f\n",
+            sparse ? "index + nonzero offsets" : "dense mab", threads, t_perm, t_pass1 - t_perm, since(tp0) - t_pass1);
   return "";
 }
 

@@ -1,6 +1,7 @@
 // Host-side format builders (see host_formats.cpp).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace sparta {
@@ -28,12 +29,29 @@ const char* host_vbr_fill(int64_t rows, int64_t cols, const int64_t* rowptr, con
 // (out->mab stays empty), the permutation, and the nonzeros as (element offset into the virtual mab,
 // value) pairs -- what the device needs to rebuild the blocks itself (28 MB instead of 4.45 GB at
 // BASELINE config #3).  Entries are grouped by block-row: block-row ib owns [nz_ptr[ib], nz_ptr[ib+1]).
+template <class T>
+struct RawBuf {                  // uninitialised storage: the filling threads touch the pages first
+  T* p = nullptr;
+  size_t n = 0;
+  RawBuf() = default;
+  RawBuf(const RawBuf&) = delete;
+  RawBuf& operator=(const RawBuf&) = delete;
+  ~RawBuf() { free(p); }
+  bool alloc(size_t count) {
+    free(p);
+    n = count;
+    p = static_cast<T*>(malloc((count ? count : 1) * sizeof(T)));
+    return p != nullptr;
+  }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
 struct HostVBRSparse {
   HostVBR index;                 // mab empty
   std::vector<int64_t> perm;     // blocked row r is original row perm[r] (rows beyond the input: padding)
   std::vector<int64_t> nz_ptr;   // [block_rows + 1]
-  std::vector<int64_t> nz_off;   // element offset of each nonzero inside the virtual mab
-  std::vector<float> nz_val;
+  RawBuf<int64_t> nz_off;        // element offset of each nonzero inside the virtual mab
+  RawBuf<float> nz_val;
 };
 const char* host_vbr_fill_sparse(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,
                                  const float* val, bool pattern_only, const int64_t* grouping, int64_t w,

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <queue>
+#include <thread>
 #include <utility>
 
 namespace sparta {
@@ -138,25 +139,22 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
     }
   }
 
-  // 2. super-rows: consecutive segments packed into one accumulator stage
+  // 2. super-rows: consecutive segments packed into one accumulator stage (sequential: cheap, and it
+  //    assigns the accumulator columns of every segment)
   const size_t nseg = st.segs.size();
-  size_t s0 = 0;
-  std::vector<std::pair<int64_t, int>> merged;  // (jb, member)
-  int32_t cols_of[kMaxMembers + 1];
-  const int64_t* slot_of[kMaxMembers];          // per member: position of jb inside its block-row
-  while (s0 < nseg) {
-    SuperRow sr{};
-    sr.seg_begin = static_cast<int32_t>(s0);
+  struct Group { size_t s0, s1; int cols; uint32_t break_mask; int64_t blocks; };
+  std::vector<Group> groups;
+  for (size_t s0 = 0; s0 < nseg;) {
     int cols = 0;
     size_t s1 = s0;
+    int64_t blocks = 0;
     while (s1 < nseg && (s1 - s0) < static_cast<size_t>(kMaxMembers) &&
            cols + st.segs[s1].h_pad <= opt.acc_cols) {
       st.segs[s1].tmem_col = cols;
-      cols_of[s1 - s0] = cols;
       cols += st.segs[s1].h_pad;
+      blocks += br.ptr[seg_src[s1].b + 1] - br.ptr[seg_src[s1].b];
       ++s1;
     }
-    cols_of[s1 - s0] = cols;
     // fixed cuts so that no MMA run spans more than 256 accumulator columns
     uint32_t break_mask = 0;
     for (size_t s = s0, run_cols = 0; s < s1; ++s) {
@@ -166,6 +164,28 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
       }
       run_cols += st.segs[s].h_pad;
     }
+    groups.push_back({s0, s1, cols, break_mask, blocks});
+    s0 = s1;
+  }
+
+  // 3.-4. per super-row: merged column-block list, chunks, run tables, pack jobs.  Super-rows are
+  //    independent, so ranges of them (balanced on block count) are built by all host threads into
+  //    partial structures whose offsets are rebased when they are appended in order: the scheduler sits
+  //    on the critical path of every create (31 ms single-threaded at BASELINE config #3).
+  const std::vector<Segment>& segs = st.segs;
+  auto build_range = [&](size_t g_lo, size_t g_hi, Structure& part) -> const char* {
+  Structure& st = part;     // everything below appends to the partial structure
+  std::vector<std::pair<int64_t, int>> merged;  // (jb, member)
+  int32_t cols_of[kMaxMembers + 1];
+  const int64_t* slot_of[kMaxMembers];          // per member: position of jb inside its block-row
+  for (size_t gi = g_lo; gi < g_hi; ++gi) {
+    const size_t s0 = groups[gi].s0, s1 = groups[gi].s1;
+    const int cols = groups[gi].cols;
+    const uint32_t break_mask = groups[gi].break_mask;
+    SuperRow sr{};
+    sr.seg_begin = static_cast<int32_t>(s0);
+    for (size_t s = s0; s < s1; ++s) cols_of[s - s0] = segs[s].tmem_col;
+    cols_of[s1 - s0] = cols;
     sr.break_mask = break_mask;
     sr.seg_count = static_cast<int32_t>(s1 - s0);
     sr.n_cols = cols;
@@ -198,7 +218,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         ++i1;
       }
       uint32_t rows_present = 0;
-      for (size_t t = i; t < i1; ++t) rows_present += st.segs[s0 + merged[t].second].h_pad;
+      for (size_t t = i; t < i1; ++t) rows_present += segs[s0 + merged[t].second].h_pad;
       // K slabs of this column block: start at the 16-byte aligned k at or below jb*w
       const int64_t q_any = slot_of[merged[i].second] - br.col.data();   // same k range for every member
       const int64_t kblk = br.blk_k0.empty() ? jb * br.w : br.blk_k0[q_any];
@@ -238,7 +258,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
             const int64_t b = seg_src[s].b;
             const int64_t q = slot_of[m] - br.col.data();
             const int lo = cols_of[m] - cols_of[mb];            // member rows inside the run
-            const int hi = lo + st.segs[s].h_pad;
+            const int hi = lo + segs[s].h_pad;
             for (int cta = 0; cta < nshare; ++cta) {
               const int r0 = std::max(lo, cta * half), r1 = std::min(hi, (cta + 1) * half);
               if (r0 >= r1) continue;
@@ -269,7 +289,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
               job.src_rs = br.blk_rs.empty() ? br.rs[b] : br.blk_rs[q];
               job.src_ks = br.blk_ks.empty() ? br.ks[b] : br.blk_ks[q];
               job.src_base = br.src[q] + (seg_src[s].row_off + (r0 - lo)) * job.src_rs;
-              job.h = std::max(0, std::min(st.segs[s].h - (r0 - lo), r1 - r0));
+              job.h = std::max(0, std::min(segs[s].h - (r0 - lo), r1 - r0));
               job.h_pad = r1 - r0;
               job.k_lo = static_cast<int32_t>(k_lo);
               job.k_w = static_cast<int32_t>(kw);
@@ -309,7 +329,72 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
     st.srows.push_back(sr);
     st.srow_cost.push_back(cost);
     st.srow_fixed.push_back(fixed);
-    s0 = s1;
+  }
+  return "";
+  };   // build_range
+
+  // ranges of super-rows balanced on block count, one per host thread
+  const size_t n_groups = groups.size();
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = static_cast<int>(std::max(1u, std::min(hw ? hw : 4u, 16u)));
+  if (st.n_blocks < 20000 || n_groups < 8) T = 1;
+  T = static_cast<int>(std::min<size_t>(T, std::max<size_t>(n_groups, 1)));
+  std::vector<size_t> cut(T + 1, 0);
+  {
+    int64_t total = 0, run = 0;
+    for (const Group& g : groups) total += g.blocks + 8;
+    int t = 1;
+    for (size_t gi = 0; gi < n_groups && t < T; ++gi) {
+      run += groups[gi].blocks + 8;
+      if (run * T >= total * t) cut[t++] = gi + 1;
+    }
+    for (; t < T; ++t) cut[t] = n_groups;
+    cut[T] = n_groups;
+  }
+  std::vector<Structure> parts(T);
+  std::vector<const char*> errs(T, "");
+  if (T == 1) {
+    errs[0] = build_range(0, n_groups, parts[0]);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t) pool.emplace_back([&, t] { errs[t] = build_range(cut[t], cut[t + 1], parts[t]); });
+    for (auto& th : pool) th.join();
+  }
+  for (int t = 0; t < T; ++t)
+    if (*errs[t]) return errs[t];
+  // append the partial structures in order, rebasing their offsets
+  for (int t = 0; t < T; ++t) {
+    Structure& pt = parts[t];
+    const uint64_t base_a = st.a_bytes;
+    const size_t base_tbl = st.tables.size(), base_chunk = st.chunks.size(), base_pass = st.pass_off.size();
+    if (((base_a + pt.a_bytes) >> 4) > UINT32_MAX) return "packed A exceeds 64 GiB";
+    if (((base_tbl + pt.tables.size()) >> 2) > UINT32_MAX) return "run tables exceed 64 GiB";
+    if (base_chunk + pt.chunks.size() > static_cast<size_t>(INT32_MAX)) return "too many chunks";
+    for (Chunk& ch : pt.chunks) {
+      ch.a_off16 += static_cast<uint32_t>(base_a >> 4);
+      ch.tbl_off16 += static_cast<uint32_t>(base_tbl >> 2);
+    }
+    for (PackJob& job : pt.jobs) job.dst_off16 += static_cast<uint32_t>(base_a >> 4);
+    for (SuperRow& sr : pt.srows) sr.chunk_begin += static_cast<int32_t>(base_chunk);
+    for (int32_t& pp : pt.pass_ptr) pp += static_cast<int32_t>(base_pass);
+    if (t == 0) {
+      st.chunks.swap(pt.chunks); st.tables.swap(pt.tables); st.jobs.swap(pt.jobs); st.chunk_cost.swap(pt.chunk_cost);
+      st.pass_off.swap(pt.pass_off); st.pass_ptr.swap(pt.pass_ptr); st.srows.swap(pt.srows);
+      st.srow_cost.swap(pt.srow_cost); st.srow_fixed.swap(pt.srow_fixed);
+    } else {
+      st.chunks.insert(st.chunks.end(), pt.chunks.begin(), pt.chunks.end());
+      st.tables.insert(st.tables.end(), pt.tables.begin(), pt.tables.end());
+      st.jobs.insert(st.jobs.end(), pt.jobs.begin(), pt.jobs.end());
+      st.chunk_cost.insert(st.chunk_cost.end(), pt.chunk_cost.begin(), pt.chunk_cost.end());
+      st.pass_off.insert(st.pass_off.end(), pt.pass_off.begin(), pt.pass_off.end());
+      st.pass_ptr.insert(st.pass_ptr.end(), pt.pass_ptr.begin(), pt.pass_ptr.end());
+      st.srows.insert(st.srows.end(), pt.srows.begin(), pt.srows.end());
+      st.srow_cost.insert(st.srow_cost.end(), pt.srow_cost.begin(), pt.srow_cost.end());
+      st.srow_fixed.insert(st.srow_fixed.end(), pt.srow_fixed.begin(), pt.srow_fixed.end());
+    }
+    st.a_bytes += pt.a_bytes;
+    st.max_chunk_bytes = std::max(st.max_chunk_bytes, pt.max_chunk_bytes);
+    st.max_chain_seen = std::max(st.max_chain_seen, pt.max_chain_seen);
   }
   st.pass_ptr.push_back(static_cast<int32_t>(st.pass_off.size()));
   if (st.chunks.size() > static_cast<size_t>(INT32_MAX)) return "too many chunks";
