@@ -357,6 +357,14 @@ int sparta_host_blocking_cached(const char* cache_dir, int64_t rows, int64_t col
                                 int32_t use_groups, int32_t force_fixed_size, int32_t flags,
                                 int64_t* grouping, sparta_blocking_stats* stats, int32_t* hit);
 
+/* The reference's -r row reorderings applied right after reading (include/matrices.h:65-82,
+ * src/general/csr.cpp:123-166): order[i] = the old index of new row i.  mode -1: ascending degree
+ * (CSR::reorder_by_degree), 2: CSR::scramble = std::random_shuffle driven by std::rand seeded from -s
+ * (include/input.h:111-114; seed 0 leaves the generator alone) -- the same glibc generator stepped the way
+ * libstdc++'s random_shuffle steps it, hence the same permutation.  mode 1 (descending degree) is refused:
+ * the reference hands std::sort a >= comparator (csr.cpp:130-133), which is undefined behaviour. */
+int sparta_host_row_order(int64_t rows, const int64_t* rowptr, int32_t mode, uint32_t seed, int64_t* order);
+
 /* get_permutation / get_partition (src/general/utilities.cpp:8-43).  perm[n]; part needs
  * n+1 slots, *part_len receives block_rows+1. */
 int sparta_host_permutation(int64_t n, const int64_t* grouping, int64_t* perm);

@@ -1986,6 +1986,13 @@ int sparta_host_blocking_cached(const char* cache_dir, int64_t rows, int64_t col
   return SPARTA_OK;
 }
 
+int sparta_host_row_order(int64_t rows, const int64_t* rowptr, int32_t mode, uint32_t seed, int64_t* order) {
+  if (rows < 0 || !rowptr || (rows && !order)) return fail(SPARTA_ERR_INVALID, "NULL rowptr or order");
+  const char* e = host_row_order(rows, rowptr, mode, seed, order);
+  if (*e) return fail(SPARTA_ERR_INVALID, e);
+  return SPARTA_OK;
+}
+
 int sparta_host_permutation(int64_t n, const int64_t* grouping, int64_t* perm) {
   if (n < 0 || (n && (!grouping || !perm))) return fail(SPARTA_ERR_INVALID, "NULL grouping or perm");
   host_permutation(grouping, n, perm);

@@ -27,6 +27,29 @@ void host_permutation(const int64_t* grouping, int64_t n, int64_t* perm) {
   std::sort(perm, perm + n, [grouping](int a, int b) { return grouping[a] < grouping[b]; });
 }
 
+const char* host_row_order(int64_t rows, const int64_t* rowptr, int32_t mode, uint32_t seed, int64_t* order) {
+  std::iota(order, order + rows, static_cast<int64_t>(0));
+  auto len = [rowptr](int i) { return rowptr[i + 1] - rowptr[i]; };
+  if (mode == 1) {
+    // the reference's descending comparator is `>=` (csr.cpp:130-133): not a strict weak order, so its
+    // std::sort call is undefined behaviour (it segfaults on a 512-row R-MAT under libstdc++ 13) and has no
+    // result to reproduce
+    return "row order 1 (-r 1, descending degree) is not provided: the reference sorts with a >= comparator";
+  } else if (mode == -1) {
+    std::sort(order, order + rows, [&](int a, int b) { return len(a) < len(b); });
+  } else if (mode == 2) {
+    if (seed != 0) std::srand(seed);
+    // std::random_shuffle (removed in C++17) as libstdc++ implements it: element i swaps with rand() % (i + 1)
+    for (int64_t i = 1; i < rows; ++i) {
+      const int64_t j = std::rand() % (i + 1);
+      if (i != j) std::swap(order[i], order[j]);
+    }
+  } else if (mode != 0) {
+    return "row order mode must be 0, 1, -1 or 2";
+  }
+  return "";
+}
+
 int64_t host_partition(const int64_t* grouping, int64_t n, int64_t* part) {
   std::vector<int64_t> g(grouping, grouping + n);
   std::sort(g.begin(), g.end());

@@ -19,6 +19,13 @@ struct HostBell {  // the out-params of prepare_cusparse_BLOCKEDELLPACK (cuda_ut
 };
 
 void host_permutation(const int64_t* grouping, int64_t n, int64_t* perm);
+
+// The reference's -r row reorderings (include/input.h:30, src/general/csr.cpp:123-166): new row i is old
+// row order[i].  mode -1: ascending degree, 2: scramble (mode 1, descending degree, is undefined behaviour in
+// the reference -- a >= comparator handed to std::sort -- and is refused).  The scramble is
+// std::random_shuffle driven by std::rand, which the reference seeds from -s (input.h:111-114); the same
+// glibc generator is seeded and stepped here (seed 0 = leave the generator as it is).
+const char* host_row_order(int64_t rows, const int64_t* rowptr, int32_t mode, uint32_t seed, int64_t* order);
 int64_t host_partition(const int64_t* grouping, int64_t n, int64_t* part);
 
 const char* host_vbr_fill(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colind,

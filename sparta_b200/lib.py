@@ -114,6 +114,7 @@ SIGNATURES = {
     "sparta_host_blocking_cached": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float,
                                               C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                               C.c_int32, _vp, _vp, C.POINTER(C.c_int32)]),
+    "sparta_host_row_order": (C.c_int, [C.c_int64, _vp, C.c_int32, C.c_uint32, _vp]),
     "sparta_host_permutation": (C.c_int, [C.c_int64, _vp, _vp]),
     "sparta_host_partition": (C.c_int, [C.c_int64, _vp, _vp, C.POINTER(C.c_int64)]),
     "sparta_host_vbr_fill": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int32,
@@ -482,6 +483,25 @@ def grouping_load(path, rows, key=0):
     g = np.zeros(rows, dtype=np.int64)
     _check(load().sparta_grouping_load(os.fsencode(path), rows, _ptr(g), int(key)))
     return g
+
+
+def host_row_order(rowptr, mode, seed=0):
+    """The reference's -r reordering (1 / -1 degree, 2 scramble with std::rand seeded by -s): order[i] = old
+    index of new row i."""
+    rowptr = _i64(rowptr)
+    order = np.zeros(len(rowptr) - 1, dtype=np.int64)
+    _check(load().sparta_host_row_order(len(order), _ptr(rowptr), int(mode), int(seed), _ptr(order)))
+    return order
+
+
+def permute_csr_rows(rowptr, colind, val, order):
+    """CSR::permute_rows (src/general/csr.cpp:66-75): new row i = old row order[i]."""
+    rowptr, colind = _i64(rowptr), _i64(colind)
+    lens = np.diff(rowptr)[order]
+    new_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = np.concatenate([np.arange(rowptr[o], rowptr[o + 1]) for o in order]) if len(order) else np.zeros(0, np.int64)
+    idx = idx.astype(np.int64)
+    return new_ptr, colind[idx], (None if val is None else np.asarray(val)[idx])
 
 
 def host_permutation(grouping):

@@ -158,3 +158,21 @@ def test_invalid_arguments(lib):
         L.host_blocking(2, 4, rowptr, np.array([0, 1, 2]), algo=1, block_col_size=2)   # -a 1 unsupported
     with pytest.raises(L.SpartaError):
         L.host_blocking(2, 4, rowptr, np.array([0, 1, 9]), algo=3, block_col_size=2)   # column out of range
+
+
+@pytest.mark.parametrize("mode,seed", [(2, 7), (2, 1), (-1, 0)])
+def test_row_reordering_matches_reference(lib, oracle, tmp_path, mode, seed):
+    """-r 1 / -1 / 2 of the reference CLI (degree sort, scramble with std::rand seeded by -s) through
+    sparta_host_row_order: the reordered CSR equals what the unmodified reference reader produces."""
+    from oracle.oracle_py import Reference
+    r, c = synth.rmat_edges(9, 5000, seed=2)
+    r, c = synth.pin_shape(r, c, 512, 512)
+    path = str(tmp_path / "m.el")
+    synth.write_el(path, r, c)
+    base = oracle.run(path, P=1, fill=False, a=2, b=8, B=8)
+    ref = (Reference() if Reference.available() else oracle).run(path, P=1, fill=False, a=2, b=8, B=8, r=mode, s=seed)
+    order = L.host_row_order(base["csr_rowptr"], mode, seed)
+    ptr, col, _ = L.permute_csr_rows(base["csr_rowptr"], base["csr_colind"], None, order)
+    assert np.array_equal(ptr, ref["csr_rowptr"]) and np.array_equal(col, ref["csr_colind"])
+    with pytest.raises(L.SpartaError):      # -r 1: a >= comparator in std::sort, undefined in the reference itself
+        L.host_row_order(base["csr_rowptr"], 1, 0)
