@@ -813,14 +813,19 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   H_TRY(upload_vec(h->st.tables, &h->d_tables, h->stream));
   H_TRY(dev_alloc(&h->d_a, h->st.a_bytes, h->stream));
   if (h->st.sparse_images && h->st.a_bytes) H_TRY(cudaMemsetAsync(h->d_a, 0, h->st.a_bytes, h->stream));
-  if (!h->st.jobs.empty()) {
-    H_TRY(upload_vec(h->st.jobs, &d_jobs, h->stream));
-    H_TRY(pack_a_images(d_src, d_jobs, static_cast<int64_t>(h->st.jobs.size()), h->d_a, o.precision, h->stream,
-                        static_cast<int64_t>(h->st.a_bytes)));
+  if (h->st.n_jobs > 0) {
+    H_TRY(dev_alloc(&d_jobs, static_cast<size_t>(h->st.n_jobs) * sizeof(PackJob), h->stream));
+    size_t at = 0;
+    for (const auto& part : h->st.job_parts) {
+      if (part.empty()) continue;
+      H_TRY(cudaMemcpyAsync(d_jobs + at, part.data(), part.size() * sizeof(PackJob), cudaMemcpyHostToDevice, h->stream));
+      at += part.size();
+    }
+    H_TRY(pack_a_images(d_src, d_jobs, h->st.n_jobs, h->d_a, o.precision, h->stream, static_cast<int64_t>(h->st.a_bytes)));
   }
   dev_free(d_src, h->stream);
   dev_free(d_jobs, h->stream);
-  std::vector<PackJob>().swap(h->st.jobs);   // pageable copies are staged before cudaMemcpyAsync returns
+  std::vector<std::vector<PackJob>>().swap(h->st.job_parts);   // pageable copies are staged before cudaMemcpyAsync returns
   H_TRY(cudaEventRecord(h->up1, h->stream));
   // The public create returns only when the caller's arrays are no longer being read.
   if (!defer_sync) H_TRY(cudaStreamSynchronize(h->stream));
@@ -2156,7 +2161,7 @@ int sparta_plan_array(sparta_plan* plan, int32_t which, const void** data, int64
     case 3: PLAN_ARR(plan->as.items, Item);
     case 4: PLAN_ARR(plan->as.cta_ptr, int32_t);
     case 5: PLAN_ARR(plan->as.cta_items, int32_t);
-    case 6: PLAN_ARR(plan->st.jobs, PackJob);
+    case 6: plan->st.merge_jobs(); PLAN_ARR(plan->st.jobs, PackJob);
     case 7: PLAN_ARR(plan->st.tables, uint32_t);
     case 8: PLAN_ARR(plan->as.zero_jobs, ZeroJob);
   }

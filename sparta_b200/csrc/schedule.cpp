@@ -6,7 +6,11 @@
 // and the per-level pointer arrays of cublas_blockmat_batched (:811-856).
 #include "schedule.h"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <queue>
 #include <thread>
 #include <utility>
@@ -75,6 +79,9 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
 
 static const char* build_structure_for(const BlockRows& br, const ScheduleOptions& opt, int64_t chain,
                                        Structure* out) {
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;
+  const auto tp0 = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count(); };
   Structure& st = *out;
   st = Structure();
   st.pair = opt.pair ? 1 : 0;
@@ -333,6 +340,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
   return "";
   };   // build_range
 
+  const double t_groups = since();
   // ranges of super-rows balanced on block count, one per host thread
   const size_t n_groups = groups.size();
   unsigned hw = std::thread::hardware_concurrency();
@@ -362,42 +370,64 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
   }
   for (int t = 0; t < T; ++t)
     if (*errs[t]) return errs[t];
-  // append the partial structures in order, rebasing their offsets
+  const double t_built = since();
+  // Append the partial structures in order, rebasing their offsets.  The pack jobs (64 bytes per image:
+  // 22 MB at BASELINE config #3) are rebased in place by all threads and kept as parts -- copying them
+  // into one array cost more than building them.
+  std::vector<uint64_t> base_a(T + 1, 0);
+  std::vector<size_t> base_tbl(T + 1, 0), base_chunk(T + 1, 0), base_pass(T + 1, 0);
+  for (int t = 0; t < T; ++t) {
+    base_a[t + 1] = base_a[t] + parts[t].a_bytes;
+    base_tbl[t + 1] = base_tbl[t] + parts[t].tables.size();
+    base_chunk[t + 1] = base_chunk[t] + parts[t].chunks.size();
+    base_pass[t + 1] = base_pass[t] + parts[t].pass_off.size();
+  }
+  if ((base_a[T] >> 4) > UINT32_MAX) return "packed A exceeds 64 GiB";
+  if ((base_tbl[T] >> 2) > UINT32_MAX) return "run tables exceed 64 GiB";
+  if (base_chunk[T] > static_cast<size_t>(INT32_MAX)) return "too many chunks";
+  {
+    auto rebase = [&](int t) {
+      Structure& pt = parts[t];
+      const uint32_t da = static_cast<uint32_t>(base_a[t] >> 4), dt = static_cast<uint32_t>(base_tbl[t] >> 2);
+      for (Chunk& ch : pt.chunks) { ch.a_off16 += da; ch.tbl_off16 += dt; }
+      for (PackJob& job : pt.jobs) job.dst_off16 += da;
+      for (SuperRow& sr : pt.srows) sr.chunk_begin += static_cast<int32_t>(base_chunk[t]);
+      for (int32_t& pp : pt.pass_ptr) pp += static_cast<int32_t>(base_pass[t]);
+    };
+    if (T == 1) {
+      rebase(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < T; ++t) pool.emplace_back(rebase, t);
+      for (auto& th : pool) th.join();
+    }
+  }
+  st.chunks.reserve(base_chunk[T]);
+  st.tables.reserve(base_tbl[T]);
+  st.chunk_cost.reserve(base_chunk[T]);
+  st.pass_off.reserve(base_pass[T]);
+  st.job_parts.clear();
   for (int t = 0; t < T; ++t) {
     Structure& pt = parts[t];
-    const uint64_t base_a = st.a_bytes;
-    const size_t base_tbl = st.tables.size(), base_chunk = st.chunks.size(), base_pass = st.pass_off.size();
-    if (((base_a + pt.a_bytes) >> 4) > UINT32_MAX) return "packed A exceeds 64 GiB";
-    if (((base_tbl + pt.tables.size()) >> 2) > UINT32_MAX) return "run tables exceed 64 GiB";
-    if (base_chunk + pt.chunks.size() > static_cast<size_t>(INT32_MAX)) return "too many chunks";
-    for (Chunk& ch : pt.chunks) {
-      ch.a_off16 += static_cast<uint32_t>(base_a >> 4);
-      ch.tbl_off16 += static_cast<uint32_t>(base_tbl >> 2);
-    }
-    for (PackJob& job : pt.jobs) job.dst_off16 += static_cast<uint32_t>(base_a >> 4);
-    for (SuperRow& sr : pt.srows) sr.chunk_begin += static_cast<int32_t>(base_chunk);
-    for (int32_t& pp : pt.pass_ptr) pp += static_cast<int32_t>(base_pass);
-    if (t == 0) {
-      st.chunks.swap(pt.chunks); st.tables.swap(pt.tables); st.jobs.swap(pt.jobs); st.chunk_cost.swap(pt.chunk_cost);
-      st.pass_off.swap(pt.pass_off); st.pass_ptr.swap(pt.pass_ptr); st.srows.swap(pt.srows);
-      st.srow_cost.swap(pt.srow_cost); st.srow_fixed.swap(pt.srow_fixed);
-    } else {
-      st.chunks.insert(st.chunks.end(), pt.chunks.begin(), pt.chunks.end());
-      st.tables.insert(st.tables.end(), pt.tables.begin(), pt.tables.end());
-      st.jobs.insert(st.jobs.end(), pt.jobs.begin(), pt.jobs.end());
-      st.chunk_cost.insert(st.chunk_cost.end(), pt.chunk_cost.begin(), pt.chunk_cost.end());
-      st.pass_off.insert(st.pass_off.end(), pt.pass_off.begin(), pt.pass_off.end());
-      st.pass_ptr.insert(st.pass_ptr.end(), pt.pass_ptr.begin(), pt.pass_ptr.end());
-      st.srows.insert(st.srows.end(), pt.srows.begin(), pt.srows.end());
-      st.srow_cost.insert(st.srow_cost.end(), pt.srow_cost.begin(), pt.srow_cost.end());
-      st.srow_fixed.insert(st.srow_fixed.end(), pt.srow_fixed.begin(), pt.srow_fixed.end());
-    }
+    st.chunks.insert(st.chunks.end(), pt.chunks.begin(), pt.chunks.end());
+    st.tables.insert(st.tables.end(), pt.tables.begin(), pt.tables.end());
+    st.chunk_cost.insert(st.chunk_cost.end(), pt.chunk_cost.begin(), pt.chunk_cost.end());
+    st.pass_off.insert(st.pass_off.end(), pt.pass_off.begin(), pt.pass_off.end());
+    st.pass_ptr.insert(st.pass_ptr.end(), pt.pass_ptr.begin(), pt.pass_ptr.end());
+    st.srows.insert(st.srows.end(), pt.srows.begin(), pt.srows.end());
+    st.srow_cost.insert(st.srow_cost.end(), pt.srow_cost.begin(), pt.srow_cost.end());
+    st.srow_fixed.insert(st.srow_fixed.end(), pt.srow_fixed.begin(), pt.srow_fixed.end());
+    st.n_jobs += static_cast<int64_t>(pt.jobs.size());
+    st.job_parts.emplace_back(std::move(pt.jobs));
     st.a_bytes += pt.a_bytes;
     st.max_chunk_bytes = std::max(st.max_chunk_bytes, pt.max_chunk_bytes);
     st.max_chain_seen = std::max(st.max_chain_seen, pt.max_chain_seen);
   }
   st.pass_ptr.push_back(static_cast<int32_t>(st.pass_off.size()));
   if (st.chunks.size() > static_cast<size_t>(INT32_MAX)) return "too many chunks";
+  if (timing)
+    fprintf(stderr, "sparta schedule: order + segments + groups %.1f ms, %d threads build %.1f, merge %.1f (%zu chunks, %zu pack jobs)\n",
+            t_groups, T, t_built - t_groups, since() - t_built, st.chunks.size(), static_cast<size_t>(st.n_jobs));
   return "";
 }
 

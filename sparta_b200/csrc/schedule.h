@@ -63,7 +63,14 @@ struct Structure {           // independent of the number of B columns
   std::vector<Segment>  segs;
   std::vector<SuperRow> srows;
   std::vector<Chunk>    chunks;
-  std::vector<PackJob>  jobs;
+  std::vector<std::vector<PackJob>> job_parts;   // the pack jobs, in order, as the scheduler's threads built them
+  int64_t n_jobs = 0;
+  std::vector<PackJob>  jobs;        // all of them in one array: filled by merge_jobs() on request only
+  void merge_jobs() {
+    if (!jobs.empty() || n_jobs == 0) return;
+    jobs.reserve(static_cast<size_t>(n_jobs));
+    for (const auto& part : job_parts) jobs.insert(jobs.end(), part.begin(), part.end());
+  }
   std::vector<uint32_t> tables;      // run tables of all chunks, back to back (see sched_types.h)
   std::vector<double>   srow_cost;   // modelled SM cycles per column tile (fixed part + chunks)
   std::vector<float>    chunk_cost;  // modelled SM cycles of every chunk
