@@ -414,9 +414,11 @@ def run_ours(args, wl):
             f"block_rows={v['block_rows']} nz_blocks={len(v['jab'])} nztot={v['nztot']}")
 
     # ---- device side: A shard resident, B replicated by ONE NCCL broadcast
-    h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
-                                    v["mab"], precision=args.precision, device=local,
-                                    block_row_begin=lo, block_row_end=hi, **tuning_opts(args))
+    def make_handle(lo_, hi_):
+        return sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
+                                           v["mab"], precision=args.precision, device=local,
+                                           block_row_begin=lo_, block_row_end=hi_, **tuning_opts(args))
+    h = make_handle(lo, hi)
     Bd = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
     Bm = None
     if rank == 0:
@@ -431,6 +433,42 @@ def run_ours(args, wl):
     else:
         t_bcast = 0.0
     h.set_B_device(Bd.data_ptr(), v["cols"], n)
+
+    # ---- the modelled partition corrected ONCE by measured shard times, only where the model is visibly
+    # off (slowest rank more than 8 % above the mean: variable-height matrices, whose gather rows and
+    # tile schedule the model prices separately).  Setup, outside every timed region.
+    rebalance = None
+    if world > 1 and args.partition == "model" and args.rebalance:
+        for _ in range(3):
+            h.run_async()
+        h.synchronize()
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ = torch.cuda.ExternalStream(h.stream, device=dev)
+        ev_a.record(s_)
+        for _ in range(5):
+            h.run_async()
+        ev_b.record(s_)
+        ev_b.synchronize()
+        mine = torch.tensor([ev_a.elapsed_time(ev_b) / 5], dtype=torch.float64, device=dev)
+        allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        measured = np.array([float(x.item()) for x in allms])
+        if measured.max() > 1.08 * measured.mean():
+            ct = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+            if rank == 0:
+                modelled = sparta_b200.partition_model_times(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"],
+                                                             v["jab"], n, cuts, precision=args.precision, **tuning_opts(args))
+                new_cuts = sparta_b200.partition_block_rows_measured(v["rows"], v["cols"], wl["w"], v["row_part"],
+                                                                     v["nzcount"], v["jab"], n, world, cuts, measured,
+                                                                     modelled, precision=args.precision, **tuning_opts(args))
+                ct.copy_(torch.from_numpy(np.asarray(new_cuts, dtype=np.int64)))
+            dist.broadcast(ct, 0)
+            rebalance = {"first_cuts": [int(c) for c in cuts], "first_ms_per_rank": measured.tolist()}
+            cuts = ct.cpu().numpy()
+            lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+            h.close()
+            h = make_handle(lo, hi)
+            h.set_B_device(Bd.data_ptr(), v["cols"], n)
     del Bd
     st = h.stats()
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
@@ -555,7 +593,8 @@ def run_ours(args, wl):
                       "sched_imbalance": st["sched_imbalance"], "grid": st["grid"], "items": st["items"],
                       "team": st["team"], "split_pieces": st["split_pieces"], "zero_tiles": st["zero_tiles"],
                       "gather_rows": st["gather_rows"], "gather_nnz": st["gather_nnz"], "chunks": st["chunks"],
-                      "shard_block_rows": [int(c) for c in cuts], "per_rank_ms_per_step": per_rank_ms},
+                      "shard_block_rows": [int(c) for c in cuts], "per_rank_ms_per_step": per_rank_ms,
+                      "rebalanced_from": rebalance},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -823,6 +862,9 @@ def main():
     ap.add_argument("--cpu-gflop-per-step", type=float, default=8.0,
                     help="--impl reference: nonzero-block GFLOP per thread-step sample")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--rebalance", type=int, default=1,
+                    help="multi-GPU: re-cut the modelled partition once with measured shard times when the slowest rank "
+                         "is more than 8 %% above the mean (0: never)")
     ap.add_argument("--partition", default="model", choices=["model", "area"],
                     help="multi-GPU block-row partition: balanced on modelled shard time (default) or on nonzero-block area")
     for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline", "gather_max_height", "gather_passes"):

@@ -178,7 +178,9 @@ int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols,
  * flattens the reference's CSR struct into, with int64 indices.  B and C default to ROW_MAJOR like
  * the reference's cuSPARSE call (:1346-1355).  The options' block_row_begin / block_row_end select
  * a range of ROWS.  SPARTA_TF32 selects plain fp32 arithmetic here (no tensor cores on this
- * path): that mode is bit-identical to CSR::multiply (src/general/csr.cpp:49-65).
+ * path): that mode is bit-identical to CSR::multiply (src/general/csr.cpp:49-65) for rows of up to 512
+ * nonzeros; longer rows are summed as 8 slices whose partial sums are added in order (same products, a
+ * different fp32 association: equal to the reference's sum within a few ulp, exactly for integer data).
  * Replaces the upload half of cusparse_gemm_custom (cuda_utilities.cpp:1251-1431, -M 2). */
 int sparta_csr_create(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
                       const int64_t* colind, const float* val, const sparta_options* opt);
@@ -306,6 +308,12 @@ int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t blo
                                          int64_t block_col_size, const int64_t* row_part,
                                          const int64_t* nzcount, const int64_t* jab, int64_t n,
                                          const sparta_options* opt, int32_t parts, int64_t* cuts);
+
+/* The model's time (SM cycles) of every shard of a GIVEN partition cuts[parts+1]: what
+ * sparta_partition_block_rows_measured needs next to the measured times. */
+int sparta_partition_model_times(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                                 const int64_t* row_part, const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                 const sparta_options* opt, int32_t parts, const int64_t* cuts, double* cycles);
 
 /* The modelled partition corrected by MEASURED times: time_scale[block_rows] holds, for every
  * block-row, measured / modelled kernel time of the shard it belonged to in an earlier partition

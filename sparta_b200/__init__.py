@@ -7,9 +7,10 @@ library or without a CUDA device raises.
 """
 from .lib import (BF16, FP16, TF32, COL_MAJOR, ROW_MAJOR, Handle, SpartaError, load,
                   partition_block_rows, partition_block_rows_measured, partition_block_rows_modelled,
+                  partition_model_times,
                   vbr_plan)
 from .api import VBR, bellpack_from_vbr, bellpack_spmm, csr_spmm, vbr_spmm, vbr_spmm_BA
 
 __all__ = ["BF16", "FP16", "TF32", "COL_MAJOR", "ROW_MAJOR", "Handle", "SpartaError", "load",
-           "partition_block_rows", "partition_block_rows_modelled", "partition_block_rows_measured", "vbr_plan", "VBR", "vbr_spmm", "bellpack_spmm",
+           "partition_block_rows", "partition_block_rows_modelled", "partition_block_rows_measured", "partition_model_times", "vbr_plan", "VBR", "vbr_spmm", "bellpack_spmm",
            "bellpack_from_vbr", "csr_spmm", "vbr_spmm_BA"]

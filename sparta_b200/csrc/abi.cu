@@ -37,6 +37,21 @@ static int fail_cuda(cudaError_t e, const char* what) {
   g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
   return SPARTA_ERR_CUDA;
 }
+// No C++ exception may cross the extern "C" boundary (ctypes, the reference's C++11 caller): the entry
+// points that allocate on the host run their bodies through this.
+template <class F>
+static int guarded(F body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return fail(SPARTA_ERR_INVALID, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(SPARTA_ERR_INVALID, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return fail(SPARTA_ERR_INVALID, "internal error");
+  }
+}
+
 // for the other translation units of the library (multi_gpu.cu)
 int sparta_internal_fail(int code, const std::string& msg) { return fail(code, msg); }
 #define CU_TRY(call)                                        \
@@ -690,7 +705,17 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   BlockRows fused;
   const BlockRows* view = &br;
   if (o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused)) view = &fused;
-  std::thread sched([&, view] { serr = build_structure(*view, h->sopt, &h->st); });
+  std::thread sched([&, view] {
+    try {
+      serr = build_structure(*view, h->sopt, &h->st);
+    } catch (...) {
+      serr = "out of host memory while building the tile schedule";
+    }
+  });
+  struct JoinGuard {   // an exception below must not reach the destructor of a joinable thread (std::terminate)
+    std::thread& t;
+    ~JoinGuard() { if (t.joinable()) t.join(); }
+  } join_guard{sched};
 
 #define H_TRY(call)                                                            \
   do {                                                                         \
@@ -1047,7 +1072,7 @@ static int vbr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int6
 int sparta_vbr_create(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
                       int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                       const int64_t* jab, const float* mab, const sparta_options* opt) {
-  return vbr_create_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false);
+  return guarded([&] { return vbr_create_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false); });
 }
 
 int sparta_vbr_create_from_csr(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
@@ -1055,8 +1080,10 @@ int sparta_vbr_create_from_csr(sparta_handle** out, int64_t rows, int64_t cols, 
                                int64_t block_col_size, int64_t row_block_size, int32_t force_fixed_size,
                                const sparta_options* opt, int64_t* dims) {
   HostVBR ix;
-  const int rc = vbr_create_from_csr_impl(out, rows, cols, rowptr, colind, val, grouping, block_col_size,
-                                          row_block_size, force_fixed_size, opt, false, &ix);
+  const int rc = guarded([&] {
+    return vbr_create_from_csr_impl(out, rows, cols, rowptr, colind, val, grouping, block_col_size, row_block_size,
+                                    force_fixed_size, opt, false, &ix);
+  });
   if (rc == SPARTA_OK && dims) {
     dims[0] = ix.rows; dims[1] = ix.cols; dims[2] = ix.block_rows; dims[3] = ix.block_cols;
     dims[4] = ix.block_col_size; dims[5] = ix.nztot;
@@ -1099,7 +1126,7 @@ static int vbr_create_ba_impl(sparta_handle** out, int64_t rows, int64_t cols, i
 int sparta_vbr_create_BA(sparta_handle** out, int64_t rows, int64_t cols, int64_t block_rows,
                          int64_t block_col_size, const int64_t* row_part, const int64_t* nzcount,
                          const int64_t* jab, const float* mab, const sparta_options* opt) {
-  return vbr_create_ba_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false);
+  return guarded([&] { return vbr_create_ba_impl(out, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, opt, false); });
 }
 
 static int bellpack_create_impl(sparta_handle** out, int64_t rows, int64_t cols, int64_t ell_blocksize,
@@ -1132,8 +1159,9 @@ int sparta_bellpack_create(sparta_handle** out, int64_t rows, int64_t cols, int6
                            int64_t ellColInd_rows, int64_t ellColInd_cols,
                            const int64_t* ellColInd, const float* ellValues,
                            const sparta_options* opt) {
-  return bellpack_create_impl(out, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd,
-                              ellValues, opt, false);
+  return guarded([&] {
+    return bellpack_create_impl(out, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd, ellValues, opt, false);
+  });
 }
 
 // CSR handles: rows of the shard [row_begin, row_end) (block_row_begin / block_row_end of the
@@ -1216,7 +1244,7 @@ static int csr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, cons
 
 int sparta_csr_create(sparta_handle** out, int64_t rows, int64_t cols, const int64_t* rowptr,
                       const int64_t* colind, const float* val, const sparta_options* opt) {
-  return csr_create_impl(out, rows, cols, rowptr, colind, val, opt, false);
+  return guarded([&] { return csr_create_impl(out, rows, cols, rowptr, colind, val, opt, false); });
 }
 
 static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device,
@@ -1314,7 +1342,7 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
 }
 
 int sparta_set_B(sparta_handle* h, const float* B, int64_t ld, int64_t n, int on_device) {
-  return set_b_impl(h, B, ld, n, on_device, false);
+  return guarded([&] { return set_b_impl(h, B, ld, n, on_device, false); });
 }
 
 static int copy_c(sparta_handle* h, float* C, int64_t ld, int on_device, bool to_handle) {
@@ -1605,7 +1633,7 @@ static int one_shot(const char* name, CreateFn create, const float* B, int64_t l
     return std::chrono::duration<double, std::milli>(b - a).count();
   };
   const auto t0 = now();
-  int rc = create(&h);
+  int rc = guarded([&] { return create(&h); });
   if (rc) return rc;
   const auto t1 = now();
   rc = set_b_impl(h, B, ldb, n, 0, true);
@@ -1680,8 +1708,11 @@ int sparta_csr_vbr_spmm(int64_t rows, int64_t cols, const int64_t* rowptr, const
   int rc = SPARTA_OK;
   if (e != cudaSuccess) rc = fail_cuda(e, "staging of B");
   sparta_handle* h = nullptr;
-  if (!rc) rc = vbr_create_from_csr_impl(&h, rows, cols, rowptr, colind, val, grouping, block_col_size, row_block_size,
-                                         force_fixed_size, &o, true, nullptr);
+  if (!rc)
+    rc = guarded([&] {
+      return vbr_create_from_csr_impl(&h, rows, cols, rowptr, colind, val, grouping, block_col_size, row_block_size,
+                                      force_fixed_size, &o, true, nullptr);
+    });
   if (!rc) {
     e = cudaStreamWaitEvent(h->stream, landed, 0);
     if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
@@ -1775,6 +1806,72 @@ int sparta_release_workspace(void) {
   return SPARTA_OK;
 }
 
+}  // extern "C"
+// Modelled time, in SM cycles, of the shard [lo, hi): the slowest worker of its tile schedule plus the
+// gather rows that run before it on the same stream.
+static const char* shard_model_cycles(int64_t block_rows, int64_t block_col_size, const int64_t* row_part,
+                                      const int64_t* nzcount, const int64_t* jab, int64_t lo, int64_t hi, int64_t cols,
+                                      int64_t n, const sparta_options& o, const ScheduleOptions& so, double* out) {
+  *out = 0;
+  if (hi <= lo) return "";
+  BlockRows br;
+  int64_t src_lo = 0, src_hi = 0;
+  const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, lo, hi, &br, &src_lo, &src_hi);
+  Structure st;
+  Assignment as;
+  BlockRows fused, tall;
+  double gather_nnz = 0;
+  const int gather_h = o.gather_max_height < 0 ? 0 : (o.gather_max_height == 0 ? 7 : o.gather_max_height);
+  const BlockRows* view = &br;
+  if (!*e && split_short_view(br, gather_h, &tall, &gather_nnz)) view = &tall;
+  const bool use_fused = !*e && o.fuse_rows != 1 && fuse_short_block_rows(*view, 16, &fused);
+  if (!*e) e = build_structure(use_fused ? fused : *view, so, &st);
+  if (!*e) e = build_assignment(st, so, n, cols, &as);
+  if (*e) return e;
+  // the gather rows: one row of B (n elements) per nonzero through the L2 at ~40 bytes per clock and SM
+  // (HBM speed when a column tile's slab of B, cols x 256 elements, is larger than the L2)
+  const double esb = so.precision == PREC_TF32 ? 4.0 : 2.0;
+  const double slab = static_cast<double>(cols) * 256.0 * esb;
+  const double rate = so.num_ctas * (slab > 100e6 ? 20.0 : 40.0);
+  *out = as.max_cta_cost + gather_nnz * static_cast<double>(n) * esb / rate;
+  return "";
+}
+
+static ScheduleOptions schedule_options_of(const sparta_options& o) {
+  ScheduleOptions so;
+  so.precision = o.precision;
+  so.seg_rows = o.seg_rows;
+  so.acc_cols = o.acc_cols;
+  so.num_ctas = o.num_ctas > 0 ? o.num_ctas : default_grid_ctas();
+  so.pair = o.cta_pair != 1;
+  so.sort_rows = o.row_order != 1;
+  so.l2_slab_bytes = static_cast<int64_t>(o.l2_slab_mb) << 20;
+  so.max_chain = o.max_chain;
+  so.split = o.split_k;
+  return so;
+}
+
+extern "C" int sparta_partition_model_times(int64_t rows, int64_t cols, int64_t block_rows, int64_t block_col_size,
+                                            const int64_t* row_part, const int64_t* nzcount, const int64_t* jab, int64_t n,
+                                            const sparta_options* opt, int32_t parts, const int64_t* cuts, double* cycles) {
+  if (block_rows < 0 || parts <= 0 || !cuts || !cycles || cols <= 0 || block_col_size <= 0 || n <= 0 ||
+      (block_rows && (!row_part || !nzcount)))
+    return fail(SPARTA_ERR_INVALID, "invalid partition request");
+  (void)rows;
+  sparta_options o;
+  resolve_options(opt, &o);
+  const ScheduleOptions so = schedule_options_of(o);
+  for (int i = 0; i < parts; ++i) {
+    if (cuts[i] < 0 || cuts[i + 1] > block_rows || cuts[i] > cuts[i + 1]) return fail(SPARTA_ERR_INVALID, "cuts out of range");
+    const char* e = shard_model_cycles(block_rows, block_col_size, row_part, nzcount, jab, cuts[i], cuts[i + 1], cols, n, o, so,
+                                       &cycles[i]);
+    if (*e) return fail(SPARTA_ERR_INVALID, e);
+  }
+  return SPARTA_OK;
+}
+
+extern "C" {
+
 // Contiguous block-row ranges balanced on the MODELLED kernel time of each shard instead of its
 // nonzero-block area: sparse block-rows cost more per FLOP (a B panel is fetched per chunk however
 // few rows share it) and every work item pays a fixed drain, so equal areas are not equal times --
@@ -1792,8 +1889,9 @@ int sparta_partition_block_rows_modelled(int64_t rows, int64_t cols, int64_t blo
                                          int64_t block_col_size, const int64_t* row_part,
                                          const int64_t* nzcount, const int64_t* jab, int64_t n,
                                          const sparta_options* opt, int32_t parts, int64_t* cuts) {
-  return partition_modelled_impl(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, opt, parts,
-                                 nullptr, cuts);
+  return guarded([&] {
+    return partition_modelled_impl(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, opt, parts, nullptr, cuts);
+  });
 }
 
 // The same with MEASURED feedback: time_scale[b] = (measured / modelled kernel time) of the shard
@@ -1806,8 +1904,9 @@ int sparta_partition_block_rows_measured(int64_t rows, int64_t cols, int64_t blo
                                          const sparta_options* opt, int32_t parts,
                                          const double* time_scale, int64_t* cuts) {
   if (!time_scale) return fail(SPARTA_ERR_INVALID, "time_scale is NULL");
-  return partition_modelled_impl(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, opt, parts,
-                                 time_scale, cuts);
+  return guarded([&] {
+    return partition_modelled_impl(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, opt, parts, time_scale, cuts);
+  });
 }
 
 static int partition_modelled_impl(int64_t rows, int64_t cols, int64_t block_rows,
@@ -1853,28 +1952,9 @@ static int partition_modelled_impl(int64_t rows, int64_t cols, int64_t block_row
     double worst = 0;
     for (int i = 0; i < parts; ++i) {
       if (cur[i + 1] <= cur[i]) continue;
-      BlockRows br;
-      int64_t src_lo = 0, src_hi = 0;
-      const char* e = blockrows_from_vbr(block_rows, block_col_size, row_part, nzcount, jab, cur[i], cur[i + 1],
-                                         &br, &src_lo, &src_hi);
-      Structure st;
-      Assignment as;
-      BlockRows fused, tall;
-      double gather_nnz = 0;
-      const int gather_h = o.gather_max_height < 0 ? 0 : (o.gather_max_height == 0 ? 7 : o.gather_max_height);
-      const BlockRows* view = &br;
-      if (!*e && split_short_view(br, gather_h, &tall, &gather_nnz)) view = &tall;
-      const bool use_fused = !*e && o.fuse_rows != 1 && fuse_short_block_rows(*view, 16, &fused);
-      if (!*e) e = build_structure(use_fused ? fused : *view, so, &st);
-      if (!*e) e = build_assignment(st, so, n, cols, &as);
+      const char* e = shard_model_cycles(block_rows, block_col_size, row_part, nzcount, jab, cur[i], cur[i + 1], cols, n, o,
+                                         so, &t[i]);
       if (*e) return fail(SPARTA_ERR_INVALID, e);
-      // the gather rows run before the tile schedule on the same stream: one row of B (n elements) per
-      // nonzero through the L2 at ~40 bytes per clock and SM (HBM speed when a column tile's slab of B,
-      // cols x 256 elements, is larger than the L2)
-      const double esb = so.precision == PREC_TF32 ? 4.0 : 2.0;
-      const double slab = static_cast<double>(cols) * 256.0 * esb;
-      const double rate = so.num_ctas * (slab > 100e6 ? 20.0 : 40.0);
-      t[i] = as.max_cta_cost + gather_nnz * static_cast<double>(n) * esb / rate;
       if (time_scale) {
         double ws = 0, w = 0;
         for (int64_t b = cur[i]; b < cur[i + 1]; ++b) { ws += weight[b] * time_scale[b]; w += weight[b]; }
@@ -2073,8 +2153,8 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
                            const sparta_options* opt) {
   if (!out) return fail(SPARTA_ERR_INVALID, "out is NULL");
   *out = nullptr;
-  if (rows < 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part)
-    return fail(SPARTA_ERR_INVALID, "invalid VBR dimensions");
+  if (rows < 0 || cols <= 0 || block_rows < 0 || block_col_size <= 0 || !row_part || (block_rows && !nzcount))
+    return fail(SPARTA_ERR_INVALID, "invalid VBR dimensions or NULL index arrays");
   sparta_options o;
   resolve_options(opt, &o);
   BlockRows br;

@@ -22,6 +22,14 @@
 //   * fp32 accumulation order of the merge statistics.
 #include "blocking.h"
 
+// `-a 5` reproduces an undefined-behaviour outcome of the reference (advancing std::set::end(),
+// src/general/blocking.cpp:509-511) by issuing the same calls against the same standard library; with
+// another std::set implementation the grouping would silently differ, so refuse to build there.
+#include <set>
+#ifndef __GLIBCXX__
+#error "sparta_b200/csrc/blocking.cpp needs libstdc++: -a 5 replays the reference's std::set calls (see run_keeper)"
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <numeric>

@@ -102,6 +102,8 @@ SIGNATURES = {
     "sparta_partition_block_rows": (C.c_int, [C.c_int64, _vp, _vp, C.c_int32, _vp]),
     "sparta_partition_block_rows_modelled": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp,
                                                        C.c_int64, C.POINTER(Options), C.c_int32, _vp]),
+    "sparta_partition_model_times": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp,
+                                               C.c_int64, C.POINTER(Options), C.c_int32, _vp, _vp]),
     "sparta_partition_block_rows_measured": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp,
                                                        C.c_int64, C.POINTER(Options), C.c_int32, _vp, _vp]),
     "sparta_host_blocking": (C.c_int, [C.c_int64, C.c_int64, _vp, _vp, C.c_int32, C.c_float, C.c_int64,
@@ -206,6 +208,17 @@ def partition_block_rows_modelled(rows, cols, block_col_size, row_part, nzcount,
     _check(load().sparta_partition_block_rows_modelled(rows, cols, len(nzcount), block_col_size, _ptr(row_part),
                                                        _ptr(nzcount), _ptr(jab), n, C.byref(o), parts, _ptr(cuts)))
     return cuts
+
+
+def partition_model_times(rows, cols, block_col_size, row_part, nzcount, jab, n, cuts, **opts):
+    """The scheduler model's time (SM cycles) of every shard of the partition `cuts`."""
+    row_part, nzcount, jab, cuts = _i64(row_part), _i64(nzcount), _i64(jab), _i64(cuts)
+    out = np.zeros(len(cuts) - 1, dtype=np.float64)
+    o = make_options(**opts)
+    _check(load().sparta_partition_model_times(rows, cols, len(nzcount), block_col_size, _ptr(row_part), _ptr(nzcount),
+                                               _ptr(jab), n, C.byref(o), len(cuts) - 1, _ptr(cuts),
+                                               out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def partition_block_rows_measured(rows, cols, block_col_size, row_part, nzcount, jab, n, parts, prev_cuts,

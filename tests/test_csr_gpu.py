@@ -201,3 +201,23 @@ def test_config3_shape_rmat_csr(lib):
     for i in [0, int(np.argmax(nnz_row)), N - 1, 12345]:
         ref = B1[colind[rowptr[i]:rowptr[i + 1]]].astype(np.float64).sum(axis=0)
         assert np.array_equal(outs[0][i], ref.astype(np.float32))
+
+
+def test_fp32_mode_long_rows_real_values(oracle, lib):
+    """The fp32 ("tf32") mode is bit-identical to CSR::multiply (src/general/csr.cpp:49-65) for rows of up
+    to 512 nonzeros; a longer row is summed as 8 slices whose partial sums are added in order -- the same
+    products in a different fp32 association.  Real values: the short rows equal the reference bit for
+    bit, the long rows within a few ulp of the row's magnitude."""
+    rng = np.random.default_rng(77)
+    rows = cols = 1200
+    rowptr, colind, val = random_csr(rng, rows, cols, 0.02, "uniform", heavy_rows=(3, 700))
+    n = 40
+    B = rng.random((cols, n), dtype=np.float32)
+    Cg, _ = csr_spmm(rows, cols, rowptr, colind, val, B, n, "tf32")
+    Cref = oracle.csr_multiply(rows, rowptr, colind, val, False, np.ascontiguousarray(B.T), n).T
+    lens = np.diff(rowptr)
+    short = lens <= 512
+    assert (~short).sum() == 2 and lens.max() == cols
+    assert np.array_equal(Cg[short], Cref[short])
+    scale = np.abs(Cref[~short]).max()
+    assert np.abs(Cg[~short] - Cref[~short]).max() <= 64 * np.finfo(np.float32).eps * scale

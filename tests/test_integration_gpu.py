@@ -99,3 +99,37 @@ def test_reference_gpu_smoke_test_on_our_library(lib):
     for l in lines[1:]:
         assert l.rstrip().endswith(" is 0"), res.stdout
     assert "END" in res.stdout
+
+
+def test_result_columns_side_file(tmp_path, lib):
+    """SPARTA_B200_CSV: the columns the reference's CSV lacks (TFLOP/s on nonzero-block FLOPs, bytes, % of the
+    tensor and HBM peaks, GPU count), one row per multiply, the CLI itself untouched."""
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_ref/cuda_multiply_b200 was not prebuilt")
+    side = tmp_path / "metrics.csv"
+    env = dict(os.environ, SPARTA_B200_CSV=str(side))
+    res = subprocess.run([BIN, "-f", os.path.join(ROOT, "tests", "golden", "rmat8.el"), "-P", "1", "-c", "96", "-w", "1",
+                          "-x", "2", "-v", "0", "-o", str(tmp_path / "res.csv"), "-M", "4", "-a", "5", "-b", "16", "-B", "16",
+                          "-t", "0.6"], capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    lines = open(side).read().strip().splitlines()
+    assert lines[0].startswith("routine,rows,cols,nz_blocks,nztot,b_cols,precision,gpus,dt_ms,effective_tflops")
+    assert len(lines) == 1 + 3                      # warm-up + 2 repetitions
+    f = dict(zip(lines[0].split(","), lines[-1].split(",")))
+    assert f["routine"] == "vbr_multiply" and f["precision"] == "fp16" and int(f["gpus"]) == 1
+    assert float(f["dt_ms"]) > 0 and float(f["effective_tflops"]) > 0 and float(f["pct_tensor_peak"]) > 0
+    ref = dict(zip(*[l.rstrip(",").split(",") for l in open(tmp_path / "res.csv").read().strip().splitlines()[:2]]))
+    assert int(f["nztot"]) == int(ref["VBR_nzcount"]) and int(f["nz_blocks"]) == int(ref["VBR_nzblocks_count"])
+
+
+def test_reference_cli_on_two_gpus(tmp_path, lib):
+    """SPARTA_GPUS=2: -M 4 of the unmodified CLI through sparta_vbr_spmm_multi (skipped on a single-GPU box)."""
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_ref/cuda_multiply_b200 was not prebuilt")
+    if lib.sparta_device_count() < 2:
+        pytest.skip("needs two sm_100 devices")
+    env = dict(os.environ, SPARTA_GPUS="2")
+    res = subprocess.run([BIN, "-f", os.path.join(ROOT, "tests", "golden", "rmat8.el"), "-P", "1", "-c", "96", "-w", "1",
+                          "-x", "2", "-v", "0", "-o", str(tmp_path / "res.csv"), "-M", "4", "-a", "5", "-b", "16", "-B", "16",
+                          "-t", "0.6"], capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
