@@ -417,7 +417,7 @@ def run_ours(args, wl):
     def make_handle(lo_, hi_):
         return sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
                                            v["mab"], precision=args.precision, device=local,
-                                           block_row_begin=lo_, block_row_end=hi_, **tuning_opts(args))
+                                           block_row_begin=lo_, block_row_end=hi_, n_hint=n, **tuning_opts(args))
     h = make_handle(lo, hi)
     Bd = torch.empty((n, v["cols"]), dtype=torch.float32, device=dev)
     Bm = None
@@ -603,7 +603,7 @@ def run_ours(args, wl):
 
 def tuning_opts(args):
     o = {}
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline", "gather_max_height", "gather_passes"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline", "gather_max_height", "gather_passes", "wide_tiles"):
         val = getattr(args, k)
         if val:
             o[k] = val
@@ -867,7 +867,7 @@ def main():
                          "is more than 8 %% above the mean (0: never)")
     ap.add_argument("--partition", default="model", choices=["model", "area"],
                     help="multi-GPU block-row partition: balanced on modelled shard time (default) or on nonzero-block area")
-    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline", "gather_max_height", "gather_passes"):
+    for k in ("seg_rows", "acc_cols", "panel_stages", "num_ctas", "cta_pair", "row_order", "l2_slab_mb", "max_chain", "split_k", "copy_warps", "fuse_rows", "pipeline", "gather_max_height", "gather_passes", "wide_tiles"):
         ap.add_argument("--" + k.replace("_", "-"), dest=k, type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

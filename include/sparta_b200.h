@@ -89,7 +89,14 @@ typedef struct sparta_options {
   int32_t gather_passes;  /* launches of the gather kernel per multiply, each over one range of A's columns (the rows
                             of B a launch reads are a smaller slab).  0/1: one (default: measured faster than 6 or 8
                             passes even at 2^18 columns, where a tile's slab of B is 268 MB), k > 1: k */
-  int32_t reserved2[1];
+  int32_t wide_tiles;    /* column tiles of B one work item covers: every pipeline stage then carries that many
+                            B panels for ONE set of A images and a super-row has 512 / wide_tiles accumulator
+                            columns.  0: the library's choice from n_hint (2 when n_hint spans >= 6 tile widths, or
+                            >= 2 and the block-rows of a super-row rarely share a column block, else 1; measured,
+                            DESIGN.md section 5), 1 / 2 / 4: forced.  Schedules with bounded accumulation chains
+                            (tf32 by default) always run one tile per item. */
+  int32_t n_hint;        /* expected number of B columns (0: unknown); only used to choose wide_tiles at create
+                            time -- the one-shot calls pass their n */
 } sparta_options;
 
 /* Statistics of a handle (all counts refer to the handle's shard). */
@@ -115,6 +122,8 @@ typedef struct sparta_stats {
   double  sched_max_cycles; /* modelled SM cycles of the worker that finishes last */
   int64_t gather_rows;     /* rows of the block-rows routed to the gather kernel (gather_max_height) */
   int64_t gather_nnz;      /* their nonzeros */
+  int32_t wide_tiles;      /* column tiles of B per work item the handle was built for (1, 2 or 4) */
+  int32_t reserved3;
 } sparta_stats;
 
 const char* sparta_last_error(void);

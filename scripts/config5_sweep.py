@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--densities", default="5e-4,2e-3,8e-3", help="element densities of the R-MAT (block density follows)")
     ap.add_argument("--ns", default="256,1024,4096,8192")
     ap.add_argument("--taus", default="0.0,0.6,1.0")
+    ap.add_argument("--wide-tiles", type=int, default=0, help="sparta_options::wide_tiles (0: the library's choice)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     import torch
@@ -50,7 +51,8 @@ def main():
                 dens = blocks / (v["block_rows"] * ((N + 63) // 64))
                 for n in [int(x) for x in args.ns.split(",")]:
                     Bm = synth.seeded_B(N, n, seed=2)
-                    h = sparta_b200.Handle.from_vbr(N, N, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"])
+                    h = sparta_b200.Handle.from_vbr(N, N, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"], n_hint=n,
+                                                    wide_tiles=args.wide_tiles)
                     h.set_B(Bm, N, n)
                     for _ in range(3):
                         h.run()
@@ -61,7 +63,7 @@ def main():
                     rec = {"rows": order, "element_density": density, "tau": tau, "n": n, "nz_blocks": blocks,
                            "block_density": dens, "ms": ms, "tflops": 2.0 * v["nztot"] * n / ms / 1e9,
                            "max_rel_err": chk["max_rel_err"], "ok": chk["ok"], "team": st["team"],
-                           "split_pieces": st["split_pieces"]}
+                           "split_pieces": st["split_pieces"], "wide_tiles": st["wide_tiles"]}
                     results.append(rec)
                     print(f"density {density:.0e} rows {order:22s} tau {tau:.1f} n {n:5d}: {blocks:6d} blocks "
                           f"({100 * dens:5.1f} % of the grid)  {ms * 1e3:8.1f} us  {rec['tflops']:7.1f} TFLOP/s  "

@@ -201,12 +201,12 @@ static int ring_bytes_for(int panel_stages) {
 // has 512-row chunks), else the byte ring.  Slots make the producer's per-chunk work short enough
 // for two copy warps to matter; chunks of 1-2 members (ER-like matrices, variable-height blockings)
 // are bound by how fast stages can be STARTED, not by bytes.
-static void pick_pipeline(uint32_t max_chunk_bytes, const sparta_options& o, int* stages, int* ring_bytes,
+static void pick_pipeline(uint32_t max_chunk_bytes, const sparta_options& o, int tiles, int* stages, int* ring_bytes,
                           int* slot_bytes, int* producers) {
   const int avail = kSmemMax - 1024 - kSmemCtrlBytes;
   const int slot = static_cast<int>((std::max<uint32_t>(max_chunk_bytes, 1024) + 1023) / 1024 * 1024);
-  const int fit = std::min(kMaxPanelStages, avail / (kPanelBytes + slot));
-  const bool slots = o.pipeline == 2 ? fit >= 2 : (o.pipeline == 1 ? false : fit >= 3);
+  const int fit = std::min(kMaxPanelStages, avail / (tiles * kPanelBytes + slot));
+  const bool slots = tiles > 1 || (o.pipeline == 2 ? fit >= 2 : (o.pipeline == 1 ? false : fit >= 3));
   if (slots) {
     *stages = fit;
     *slot_bytes = slot;
@@ -527,6 +527,43 @@ static bool split_short_view(const BlockRows& br, int max_height, BlockRows* tal
   return any;
 }
 
+// The tile schedule, with the number of column tiles per work item (sparta_options::wide_tiles) chosen
+// here when the caller left it open.  Measured on B200 (profiles/r2_wide_items.md): two tiles per item
+// are 5-14 % faster than one on every bf16 shape tried once n spans 8 tile widths (2048 columns for CTA
+// pairs: config #3 3.09 -> 2.85 ms), neutral (-5..+6 %) at 4 widths, and at 2-4 widths they pay only
+// when the member block-rows of a super-row rarely share a column block (ER-like lists: a B panel feeds
+// one block, and the rate at which stages can be STARTED, not their bytes, bounds the pipeline --
+// config #2 0.122 -> 0.099 ms).  Four tiles per item were slower everywhere but there (and not the
+// best there either).  So: n_hint >= 6 tile widths -> 2 tiles; 2..6 widths -> 2 tiles when a first build
+// with one tile shows fewer than 1.6 members per chunk; unknown or small n -> 1.  Schedules that need
+// bounded accumulation chains (tf32 by default) keep one tile: the master accumulators need the room.
+static const char* build_structure_choosing_tiles(const BlockRows& view, const sparta_options& o, ScheduleOptions* so,
+                                                  Structure* st) {
+  const int tile_w = so->pair ? 2 * kTileJ : kTileJ;
+  auto build_with = [&](int tiles, Structure* out) {
+    ScheduleOptions s2 = *so;
+    s2.tiles = tiles;
+    if (tiles > 1) s2.acc_cols = 512 / tiles;
+    const char* e = build_structure(view, s2, out);      // (falls back to one tile if chains must be bounded)
+    if (!*e && out->tiles == tiles && tiles > 1) so->tiles = tiles, so->acc_cols = s2.acc_cols;
+    return e;
+  };
+  if (o.wide_tiles == 2 || o.wide_tiles == 4) return build_with(o.wide_tiles, st);
+  if (so->acc_cols != 256 && so->acc_cols != 512) return "acc_cols must be 256 or 512";
+  const bool open = o.wide_tiles == 0 && so->acc_cols == 512 && o.n_hint >= 2 * tile_w;
+  if (open && o.n_hint >= 6 * tile_w) return build_with(2, st);
+  const char* e = build_structure(view, *so, st);
+  if (*e || !open || st->master_col > 0 || st->chunks.empty()) return e;
+  double members = 0;
+  for (const Chunk& ch : st->chunks) members += __builtin_popcount(ch.mask);
+  members /= static_cast<double>(st->chunks.size());
+  if (members >= 1.6) return e;
+  Structure wide;
+  const char* e2 = build_with(2, &wide);
+  if (!*e2 && wide.tiles == 2) *st = std::move(wide);
+  return e;
+}
+
 // ---- handle construction ---------------------------------------------------
 
 static void free_handle(sparta_handle* h) {
@@ -707,7 +744,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   if (o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused)) view = &fused;
   std::thread sched([&, view] {
     try {
-      serr = build_structure(*view, h->sopt, &h->st);
+      serr = build_structure_choosing_tiles(*view, o, &h->sopt, &h->st);
     } catch (...) {
       serr = "out of host memory while building the tile schedule";
     }
@@ -831,7 +868,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
                 : "a chunk's A images exceed the shared-memory ring; lower acc_cols or panel_stages");
   }
   h->rows = h->st.rows;
-  pick_pipeline(h->st.max_chunk_bytes, o, &h->panel_stages, &h->a_ring_bytes, &h->a_slot_bytes, &h->producers);
+  pick_pipeline(h->st.max_chunk_bytes, o, h->st.tiles, &h->panel_stages, &h->a_ring_bytes, &h->a_slot_bytes, &h->producers);
   H_TRY(upload_vec(h->st.segs, &h->d_segs, h->stream));
   H_TRY(upload_vec(h->st.srows, &h->d_srows, h->stream));
   H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
@@ -1484,7 +1521,8 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
   p.a_ring_bytes = h->a_ring_bytes;
   // bounded chains: 256 working columns + 256 master columns, one accumulator stage
   p.master_col = h->st.master_col;
-  p.acc_stages = h->st.master_col > 0 ? 1 : 512 / h->st.acc_cols;
+  p.tiles = h->st.tiles;
+  p.acc_stages = (h->st.master_col > 0 || h->st.tiles > 1) ? 1 : 512 / h->st.acc_cols;
   p.acc_stage_cols = h->st.acc_cols;
   const char* err = "";
   if (!h->as.zero_jobs.empty() && !h->accumulate) {
@@ -1576,10 +1614,11 @@ static void fill_stats(const Structure& st, const Assignment& as, int64_t cols, 
   s->items = static_cast<int64_t>(as.items.size());
   s->a_packed_bytes = static_cast<int64_t>(st.a_bytes);
   s->grid = as.grid;
-  s->smem_bytes = spmm_smem_bytes(panel_stages, a_ring_bytes);
+  s->smem_bytes = spmm_smem_bytes(panel_stages, a_ring_bytes, st.tiles);
   s->sched_imbalance = as.mean_cta_cost > 0 ? as.max_cta_cost / as.mean_cta_cost : 1.0;
   s->team = as.team;
   s->cta_pair = st.pair;
+  s->wide_tiles = st.tiles;
   s->split_pieces = as.split_pieces;
   s->zero_tiles = static_cast<int32_t>(as.zero_jobs.size());
   s->sched_max_cycles = as.max_cta_cost;
@@ -1669,6 +1708,7 @@ int sparta_vbr_spmm(int64_t rows, int64_t cols, int64_t block_rows, int64_t bloc
   memset(&o, 0, sizeof(o));
   o.struct_size = sizeof(o);
   o.precision = precision;
+  o.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));
   return one_shot("sparta_vbr_spmm", [&](sparta_handle** h) {
     return vbr_create_impl(h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o, true);
   }, B, ldb, n, C, ldc, dt_ms);
@@ -1682,6 +1722,7 @@ int sparta_csr_vbr_spmm(int64_t rows, int64_t cols, const int64_t* rowptr, const
   memset(&o, 0, sizeof(o));
   o.struct_size = sizeof(o);
   o.precision = precision;
+  o.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));
   // B starts crossing PCIe BEFORE the host builds the index arrays and the tile schedule (tens of ms on
   // the CPU): a staging buffer on a side stream of the current device, handed to set_B as a device
   // operand once the handle exists.
@@ -1755,6 +1796,7 @@ int sparta_vbr_spmm_BA(int64_t rows, int64_t cols, int64_t block_rows, int64_t b
   memset(&o, 0, sizeof(o));
   o.struct_size = sizeof(o);
   o.precision = precision;
+  o.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));
   return one_shot("sparta_vbr_spmm_BA", [&](sparta_handle** h) {
     return vbr_create_ba_impl(h, rows, cols, block_rows, block_col_size, row_part, nzcount, jab, mab, &o, true);
   }, B, ldb, n, C, ldc, dt_ms);
@@ -1769,6 +1811,7 @@ int sparta_bellpack_spmm(int64_t rows, int64_t cols, int64_t ell_blocksize,
   memset(&o, 0, sizeof(o));
   o.struct_size = sizeof(o);
   o.precision = precision;
+  o.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));
   return one_shot("sparta_bellpack_spmm", [&](sparta_handle** h) {
     return bellpack_create_impl(h, rows, cols, ell_blocksize, ellColInd_rows, ellColInd_cols, ellColInd,
                                 ellValues, &o, true);
@@ -1825,8 +1868,11 @@ static const char* shard_model_cycles(int64_t block_rows, int64_t block_col_size
   const BlockRows* view = &br;
   if (!*e && split_short_view(br, gather_h, &tall, &gather_nnz)) view = &tall;
   const bool use_fused = !*e && o.fuse_rows != 1 && fuse_short_block_rows(*view, 16, &fused);
-  if (!*e) e = build_structure(use_fused ? fused : *view, so, &st);
-  if (!*e) e = build_assignment(st, so, n, cols, &as);
+  ScheduleOptions so2 = so;
+  sparta_options o2 = o;
+  o2.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));
+  if (!*e) e = build_structure_choosing_tiles(use_fused ? fused : *view, o2, &so2, &st);
+  if (!*e) e = build_assignment(st, so2, n, cols, &as);
   if (*e) return e;
   // the gather rows: one row of B (n elements) per nonzero through the L2 at ~40 bytes per clock and SM
   // (HBM speed when a column tile's slab of B, cols x 256 elements, is larger than the L2)
@@ -2179,7 +2225,9 @@ int sparta_vbr_plan_create(sparta_plan** out, int64_t rows, int64_t cols, int64_
   {
     BlockRows fused;
     const bool use_fused = o.fuse_rows != 1 && fuse_short_block_rows(br, 16, &fused);
-    e = build_structure(use_fused ? fused : br, p->sopt, &p->st);
+    sparta_options o2 = o;
+    o2.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));   // a plan knows its n
+    e = build_structure_choosing_tiles(use_fused ? fused : br, o2, &p->sopt, &p->st);
   }
   if (!*e) e = build_assignment(p->st, p->sopt, n, cols, &p->as);
   if (*e) { delete p; return fail(SPARTA_ERR_INVALID, e); }

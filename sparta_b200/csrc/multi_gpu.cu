@@ -107,6 +107,7 @@ extern "C" int sparta_vbr_spmm_multi(int64_t rows, int64_t cols, int64_t block_r
   memset(&base, 0, sizeof(base));
   base.struct_size = sizeof(base);
   base.precision = precision;
+  base.n_hint = static_cast<int32_t>(std::min<int64_t>(n, INT32_MAX));
   std::vector<int64_t> cuts(n_gpus + 1, 0);
   int rc = sparta_partition_block_rows_modelled(rows, cols, block_rows, block_col_size, row_part, nzcount, jab, n, &base,
                                                 n_gpus, cuts.data());

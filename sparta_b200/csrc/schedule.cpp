@@ -74,6 +74,7 @@ const char* build_structure(const BlockRows& br, const ScheduleOptions& opt, Str
   if (*e || chain < 0 || out->max_chain_seen <= chain) return e;
   ScheduleOptions o2 = opt;
   o2.acc_cols = 256;
+  o2.tiles = 1;            // bounded chains keep the master accumulators in the other half of TMEM
   return build_structure_for(br, o2, chain, out);
 }
 
@@ -85,13 +86,17 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
   Structure& st = *out;
   st = Structure();
   st.pair = opt.pair ? 1 : 0;
+  st.tiles = opt.tiles;
   st.acc_cols = opt.acc_cols;
   st.master_col = chain > 0 ? 256 : 0;
   st.chain = chain;
   st.sparse_images = !br.sub_ptr.empty();
   if (br.w <= 0) return "column block size must be positive";
   if (opt.seg_rows < 16 || opt.seg_rows > 256 || opt.seg_rows % 16) return "seg_rows must be a multiple of 16 in [16,256]";
-  if (opt.acc_cols != 256 && opt.acc_cols != 512) return "acc_cols must be 256 or 512";
+  if (opt.tiles != 1 && opt.tiles != 2 && opt.tiles != 4) return "tiles must be 1, 2 or 4";
+  if (opt.tiles > 1 && (opt.acc_cols != 512 / opt.tiles || chain > 0))
+    return "wide items need acc_cols = 512 / tiles and unbounded accumulation chains";
+  if (opt.acc_cols != 128 && opt.acc_cols != 256 && opt.acc_cols != 512) return "acc_cols must be 128, 256 or 512";
   if (opt.seg_rows > opt.acc_cols) return "seg_rows exceeds acc_cols";
   const int esize = prec_esize(opt.precision);
   const int katom = 128 / esize;    // k elements per 128-byte swizzle row
@@ -209,7 +214,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
     // Per work item: draining the accumulator (measured 20.4 k cycles for 512 columns while the
     // other SMs keep the L2 busy; the stores, not the TMEM reads, are the limit -- see
     // scripts/microbench/epilogue_rate.cu) plus the tensor pipe running dry and refilling.
-    const double fixed = 16000.0 + 40.0 * cols;
+    const double fixed = 16000.0 + 40.0 * cols * opt.tiles;   // a wide item drains `tiles` copies of the columns
     double cost = fixed;
     size_t i = 0;
     while (i < merged.size()) {
@@ -322,8 +327,8 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
         // times of 30 shards of the bench matrix (scripts/fit_cost_model.py): 511 cycles per chunk
         // + 1.25 per staged row of A in pair mode (64 bytes per row and CTA => ~50 B/cycle/SM),
         // 36.7 k per item
-        const double tensor = ch.ksteps * (rows_present * 0.5);
-        const double memory = 183.0 + (kPanelBytes + share) / 50.0;
+        const double tensor = ch.ksteps * (rows_present * 0.5) * opt.tiles;
+        const double memory = 183.0 + (opt.tiles * kPanelBytes + share) / 50.0;
         st.chunk_cost.push_back(static_cast<float>(std::max(tensor, memory)));
         cost += st.chunk_cost.back();
       }
@@ -632,7 +637,7 @@ const char* build_assignment(const Structure& st, const ScheduleOptions& opt, in
                              int64_t k_total, Assignment* out) {
   Assignment& as = *out;
   as = Assignment();
-  const int tile = st.pair ? 2 * kTileJ : kTileJ;
+  const int tile = (st.pair ? 2 * kTileJ : kTileJ) * st.tiles;   // columns of B one work item covers
   if (n <= 0 || n > INT32_MAX - tile) return "invalid number of B columns";
   const int64_t tiles = (n + tile - 1) / tile;
   const int64_t n_srows = static_cast<int64_t>(st.srows.size());

@@ -51,6 +51,8 @@ struct ScheduleOptions {
   int precision = PREC_BF16;
   int seg_rows = 64;       // max rows per segment (multiple of 16, <= 256)
   int acc_cols = 512;      // TMEM columns per accumulator stage: 256 (2 stages) or 512 (1)
+  int tiles = 1;           // column tiles of B one work item covers (1, 2 or 4): every stage then carries `tiles`
+                           // panels of B for ONE set of A images, and a super-row gets 512 / tiles accumulator columns
   int num_ctas = 148;      // persistent grid size upper bound
   int pair = 1;            // 1: two CTAs (one TPC) share a super-row through tcgen05 cta_group::2
   int sort_rows = 1;       // 1: group block-rows of similar nonzero-block count into super-rows
@@ -87,6 +89,7 @@ struct Structure {           // independent of the number of B columns
   int64_t  rows = 0;                 // C rows covered by the shard
   uint32_t max_chunk_bytes = 0;      // largest per-CTA chunk (what must fit in the smem ring)
   int pair = 0;
+  int tiles = 1;                     // column tiles per work item the super-rows were packed for (ScheduleOptions::tiles)
   bool sparse_images = false;        // jobs write only their own rows: the image buffer must be zeroed first
 };
 

@@ -304,9 +304,11 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   uint8_t* smem = smem_raw + (base - raw_addr);
 
   const int P = p.panel_stages;
+  const int T = kSlots ? p.tiles : 1;                 // B panels per stage (column tiles per work item)
+  const uint32_t stage_panels = static_cast<uint32_t>(T) * kPanelBytes;
   const uint32_t panels = base;
-  const uint32_t a_ring = base + P * kPanelBytes;
-  uint8_t* ctrl = smem + P * kPanelBytes + p.a_ring_bytes;
+  const uint32_t a_ring = base + P * stage_panels;
+  uint8_t* ctrl = smem + P * stage_panels + p.a_ring_bytes;
   const uint32_t ctrl_u = a_ring + p.a_ring_bytes;
   // ctrl layout: full[8] | empty[8] | acc_full[2] | acc_empty[2] | tmem_ptr | starts[8] |
   //              run tables[8] (kTableBytes each, filled by the copy engine)
@@ -412,8 +414,10 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
               const uint32_t full = bar_full + 8 * slot;
               const uint8_t* src = p.a_packed + static_cast<size_t>(ch_off16) * 16 + static_cast<size_t>(rank) * bytes;
               const uint32_t dst = a_ring + slot * slot_bytes;
-              mbar_arrive_expect_tx(full, kPanelBytes + bytes + tb_bytes);
-              tma_load_2d(panels + slot * kPanelBytes, &tmap_b, ch_k0, j0, full);
+              mbar_arrive_expect_tx(full, stage_panels + bytes + tb_bytes);
+              for (int t = 0; t < T; ++t)   // tile t of the item: columns j0 + t * (tile width); beyond n the box is zero-filled
+                tma_load_2d(panels + slot * stage_panels + t * kPanelBytes, &tmap_b, ch_k0,
+                            j0 + t * (kPair ? 2 * kTileJ : kTileJ), full);
               for (uint32_t done = 0; done < bytes; done += 32768u) {
                 const uint32_t piece = min(32768u, bytes - done);
                 bulk_load(dst + done, src + done, piece, full);
@@ -560,19 +564,22 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             const uint4 r01 = tbl[1];            // runs 0 and 1: {idesc, where} x 2
             const uint4 r23 = tbl[2];            // runs 2 and 3 (slot is always kTableBytes long)
             const uint32_t a_base = kSlots ? a_ring + s * static_cast<uint32_t>(p.a_slot_bytes) : a_ring + starts[s];
-            const uint64_t pdesc = smem_desc(panels + s * kPanelBytes);
+            const uint64_t pdesc0 = smem_desc(panels + s * stage_panels);
             const int nruns = static_cast<int>(hdr.x);
             const int ksteps = static_cast<int>(hdr.y);
             auto fire = [&](uint32_t idesc, uint32_t where) {
               const uint64_t adesc = smem_desc(a_base + ((where & 0xFFFFu) << 4));
-              const uint32_t d_tmem = acc_base + (where >> 16);
-              if (ksteps == 4) {
+              for (int t = 0; t < T; ++t) {      // the same rows of A against every B panel of the stage
+                const uint64_t pdesc = pdesc0 + static_cast<uint64_t>(t) * (kPanelBytes >> 4);
+                const uint32_t d_tmem = acc_base + static_cast<uint32_t>(t) * static_cast<uint32_t>(p.acc_stage_cols) + (where >> 16);
+                if (ksteps == 4) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle row
-                  tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
-              } else {
-                for (int k = 0; k < ksteps; ++k)
-                  tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
+                  for (int k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle row
+                    tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
+                } else {
+                  for (int k = 0; k < ksteps; ++k)
+                    tc_mma<kTf32, kPair>(d_tmem, pdesc + 2 * k, adesc + 2 * k, idesc);
+                }
               }
             };
             fire(r01.x, r01.y);
@@ -625,7 +632,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       // this CTA's share of the tiles that split pieces add into (see SpmmParams::zero_jobs);
       // it runs while the producer and MMA warps work on the first item
       const int et = static_cast<int>(threadIdx.x) - 64;   // 0..127 over the four epilogue warps
-      constexpr int kHalves = kPair ? 2 : 1;
+      const int kHalves = (kPair ? 2 : 1) * T;   // 128-column pieces of one (wide) tile
       for (int u = blockIdx.x; u < p.n_zero_jobs * kHalves; u += gridDim.x) {
         const ZeroJob job = p.zero_jobs[u / kHalves];
         const int j0 = job.j0 + (u % kHalves) * kTileJ;
@@ -692,9 +699,10 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       const unsigned long long te0 = (tr && warp == 2 && lane == 0) ? sm_clock() : 0ull;
       ++acc_use[as];
       tc_fence_after();
-      const uint32_t t_acc = t_lane + as * p.acc_stage_cols;
-      const int j = item.j0 + static_cast<int>(rank) * kTileJ + q * 32 + lane;
-      const bool jv = j < p.n;
+      // (tile 0 of the item; a wide item drains its other column tiles below, updating these four)
+      uint32_t t_acc = t_lane + as * p.acc_stage_cols;
+      int j = item.j0 + static_cast<int>(rank) * kTileJ + q * 32 + lane;
+      bool jv = j < p.n;
       float* cj = p.C + static_cast<int64_t>(j) * p.c_sj;
       // The segment records of the super-row, one per lane, broadcast by shuffle below: a global
       // load per segment inside the loop put an L2 round trip on the critical path of the drain.
@@ -788,6 +796,13 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
         // step s+1 is in flight while step s is stored; tcgen05.wait::ld sits right before the
         // first use of a buffer and nothing touches the buffer between its load and that wait.
         const int nsteps = sr.n_cols >> 4;
+        for (int t = 0; t < T; ++t) {
+        if (t > 0) {   // next column tile of a wide item: its accumulators sit acc_stage_cols further
+          t_acc += static_cast<uint32_t>(p.acc_stage_cols);
+          j += kPair ? 2 * kTileJ : kTileJ;
+          jv = j < p.n;
+          cj = p.C + static_cast<int64_t>(j) * p.c_sj;
+        }
         int sidx = 0, c0 = 0;
         Segment sg = segment(0);
         auto advance = [&]() {
@@ -809,6 +824,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
             store16(vb, sg, c0);
             advance();
           }
+        }
         }
       }
       tmem_wait_st();
@@ -917,7 +933,13 @@ cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
     *err = "cuTensorMapEncodeTiled failed for the B operand";
     return cudaErrorInvalidValue;
   }
-  const int smem = spmm_smem_bytes(p.panel_stages, p.a_ring_bytes);
+  const int tiles = p.a_slot_bytes > 0 ? p.tiles : 1;
+  if (tiles != 1 && tiles != 2 && tiles != 4) { *err = "tiles must be 1, 2 or 4"; return cudaErrorInvalidConfiguration; }
+  if (tiles > 1 && (p.acc_stages != 1 || p.acc_stage_cols * tiles != 512 || p.master_col != 0)) {
+    *err = "wide items need one accumulator stage of 512 / tiles columns";
+    return cudaErrorInvalidConfiguration;
+  }
+  const int smem = spmm_smem_bytes(p.panel_stages, p.a_ring_bytes, tiles);
   if (smem > kSmemMax || p.panel_stages < 2 || p.panel_stages > kMaxPanelStages) {
     *err = "invalid pipeline configuration (shared memory)";
     return cudaErrorInvalidConfiguration;

@@ -30,6 +30,8 @@ struct SpmmParams {
   int32_t         a_slot_bytes; // > 0: fixed-slot pipeline, every stage owns this many bytes for its A images
                                 //      (a_ring_bytes = panel_stages * a_slot_bytes); 0: byte ring
   int32_t         producers;    // copy-issuing warps per CTA: 1, or 2 (fixed slots only; alternate chunks)
+  int32_t         tiles;        // column tiles of B per work item (fixed slots only): every stage holds `tiles` B panels
+                                // for one set of A images; tile t accumulates in TMEM columns [t * 512 / tiles, ...)
   // Split pieces (kItemAtomic) add into C tiles that must start from zero.  Every CTA zeroes its
   // share of those tiles in its epilogue warps while its first item is still in the tensor pipe,
   // then bumps *sync_counter; a warp about to issue its first reduction waits until the counter
@@ -55,8 +57,8 @@ constexpr int kSmemMax       = 232448; // 227 KB opt-in limit per CTA
 
 // Bytes of dynamic shared memory for a configuration (includes 1 KB slack used
 // to align the base to 1024 for SWIZZLE_128B).
-static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes) {
-  return 1024 + panel_stages * kPanelBytes + a_ring_bytes + kSmemCtrlBytes;
+static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes, int tiles = 1) {
+  return 1024 + panel_stages * tiles * kPanelBytes + a_ring_bytes + kSmemCtrlBytes;
 }
 
 // B operand as the kernel reads it: [n][ldk] elements (k contiguous), converted

@@ -30,7 +30,7 @@ class Options(C.Structure):
         ("num_ctas", C.c_int32), ("block_row_begin", C.c_int64), ("block_row_end", C.c_int64),
         ("cta_pair", C.c_int32), ("row_order", C.c_int32), ("l2_slab_mb", C.c_int32),
         ("max_chain", C.c_int32), ("split_k", C.c_int32), ("fuse_rows", C.c_int32),
-        ("explicit_range", C.c_int32), ("pipeline", C.c_int32), ("copy_warps", C.c_int32), ("gather_max_height", C.c_int32), ("gather_passes", C.c_int32), ("reserved2", C.c_int32 * 1),
+        ("explicit_range", C.c_int32), ("pipeline", C.c_int32), ("copy_warps", C.c_int32), ("gather_max_height", C.c_int32), ("gather_passes", C.c_int32), ("wide_tiles", C.c_int32), ("n_hint", C.c_int32),
     ]
 
 
@@ -44,6 +44,7 @@ class Stats(C.Structure):
         ("upload_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("team", C.c_int32), ("cta_pair", C.c_int32), ("split_pieces", C.c_int32), ("zero_tiles", C.c_int32),
         ("sched_max_cycles", C.c_double), ("gather_rows", C.c_int64), ("gather_nnz", C.c_int64),
+        ("wide_tiles", C.c_int32), ("reserved3", C.c_int32),
     ]
 
     def as_dict(self):

@@ -64,7 +64,10 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
     visited = np.zeros(len(items), dtype=bool)
     assert len(plan["cta_ptr"]) - 1 == plan["stats"]["grid"] // nshare
     NOT_FIRST, NOT_LAST, ATOMIC, COUNT = 1 << 31, 1 << 30, 1 << 29, (1 << 29) - 1
-    tile = 128 * nshare
+    T = int(plan["stats"].get("wide_tiles", 1)) or 1     # column tiles per work item (wide items)
+    tile = 128 * nshare * T
+    if T > 1:
+        assert int(srows["n_cols"].max()) <= 512 // T
     # zero_c_tiles_kernel: the tiles split pieces add into start from zero
     zeroed = set()
     for job in plan["zero_jobs"]:
@@ -114,8 +117,12 @@ def run_plan(plan, mab, Bm, cols, n, rows, esize=2):
                     n_atomic += 1
             if fold_in or to_master:   # working + master accumulators must both fit in TMEM
                 assert int(sr["n_cols"]) <= 256
-            for cta in range(nshare):      # each CTA of a pair owns 128 of the item's columns
-                j0 = int(item["j0"]) + cta * 128
+            if T > 1:
+                assert not (fold_in or to_master), "wide items have no room for master accumulators"
+            # each CTA of a pair owns 128 of the columns of every tile of the item; the T tiles of a wide item
+            # accumulate side by side in TMEM (same arithmetic, one accumulator each)
+            for cta, t in [(c, t) for t in range(T) for c in range(nshare)]:
+                j0 = int(item["j0"]) + t * 128 * nshare + cta * 128
                 jj = max(0, min(128, n - j0))
                 acc = np.zeros((128, int(sr["n_cols"])), dtype=np.float32)
                 for ch in chunks[sr["chunk_begin"] + off:sr["chunk_begin"] + off + cnt]:

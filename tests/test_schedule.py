@@ -18,6 +18,10 @@ CASES = [
     (2, 64, 32, [200, 70], 1.0, 8, {"seg_rows": 64}),            # tall block-rows split into segments
     (40, 64, 8, [1] * 40, 0.3, 8, {"acc_cols": 512}),            # many height-1 block-rows
     (3, 64, 16, [5, 0, 9], 0.9, 8, {}),                          # an empty block-row
+    (7, 128, 64, [64] * 7, 0.4, 600, {"wide_tiles": 2}),         # wide items: 2 column tiles per item, 256 acc columns
+    (11, 256, 64, [64, 16, 64, 48, 64, 64, 32, 64, 64, 80, 64], 0.5, 1100, {"wide_tiles": 4, "row_order": 1}),
+    (40, 64, 8, [1] * 40, 0.3, 520, {"wide_tiles": 4}),          # 4 tiles, the last ones beyond n in pair mode
+    (9, 512, 64, [64] * 9, 0.15, 1024, {}),                      # ER-like lists: the library picks wide items itself
 ]
 
 
@@ -187,13 +191,16 @@ def test_split_is_chosen_only_when_it_pays(lib):
     rng = np.random.default_rng(32)
     # few heavy super-rows for many workers: whole units cannot fill the grid
     v = random_vbr(rng, 24, 8192, 64, [64] * 24, 0.8, values="int")
-    few = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048)
-    never = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048, split_k=1)
+    few = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048, wide_tiles=1)
+    never = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048, split_k=1, wide_tiles=1)
     assert few["stats"]["split_pieces"] > 0 and never["stats"]["split_pieces"] == 0
     # whole units keep 24 of the 74 CTA pairs busy; the split plan fills the grid evenly (9 teams of
     # 8 column tiles and the 2 leftover pairs as a narrow tenth team)
     assert never["stats"]["grid"] == 48 and few["stats"]["grid"] == 148 and few["stats"]["team"] == 8
     assert few["stats"]["sched_imbalance"] < 1.25
+    # (the library's own choice at n = 2048 is two column tiles per item: 6 super-rows x 4 wide tiles, split the same way)
+    wide = sparta_b200.vbr_plan(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], 2048)
+    assert wide["stats"]["wide_tiles"] == 2 and wide["stats"]["split_pieces"] > 0 and wide["stats"]["grid"] == 148
     # many units per worker: list scheduling is already balanced, nothing is split
     v = random_vbr(rng, 400, 1024, 64, [64] * 400, 0.3, values="int")
     many = sparta_b200.vbr_plan(v["rows"], 1024, 64, v["row_part"], v["nzcount"], v["jab"], 2048, num_ctas=16)

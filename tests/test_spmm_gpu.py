@@ -300,6 +300,105 @@ def test_tf32_long_positive_sums_within_1e5(lib):
     assert rel_err(Cu, ref) <= TOL_UNROUNDED["tf32"]
 
 
+WIDE_CASES = [
+    # block_rows, cols, w, heights, density, n, wide_tiles, extra
+    (7, 128, 64, [64] * 7, 0.4, 600, 2, {}),
+    (11, 256, 64, [64, 16, 64, 48, 64, 64, 32, 64, 64, 80, 64], 0.5, 1100, 4, {"row_order": 1}),
+    (40, 64, 8, [1] * 40, 0.3, 520, 4, {"gather_max_height": -1}),      # tail tiles beyond n, height-1 block-rows on MMAs
+    (48, 2048, 64, [64] * 45 + [63, 30, 7], 0.12, 1500, 2, {"num_ctas": 8}),   # many items per worker, the slots wrap
+    (48, 2048, 64, [64] * 48, 0.12, 2048, 4, {}),                       # the ER shape of config #2, scaled down
+    (9, 640, 64, [64, 63, 30, 64, 1, 128, 7, 64, 33], 0.7, 777, 2, {"gather_max_height": -1}),
+]
+
+
+@pytest.mark.parametrize("mode", ["single", "pair"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
+@pytest.mark.parametrize("case", range(len(WIDE_CASES)))
+def test_wide_items_bit_exact(oracle, lib, case, precision, mode):
+    """wide_tiles = 2 / 4: a work item covers that many column tiles, every pipeline stage carries that many
+    panels of B for one set of A images, the tiles accumulate side by side in TMEM (512 / wide_tiles columns
+    each) and are drained one after the other.  Integer operands: bit-exact."""
+    block_rows, cols, w, heights, density, n, tiles, extra = WIDE_CASES[case]
+    rng = np.random.default_rng(900 + case)
+    v = random_vbr(rng, block_rows, cols, w, heights, density, values="int")
+    Bm = rng.integers(-3, 4, size=(n, cols)).astype(np.float32)
+    h = sparta_b200.Handle.from_vbr(v["rows"], cols, w, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    precision=precision, wide_tiles=tiles, max_chain=-1, **dict(extra, **MODES[mode]))
+    try:
+        h.set_B(Bm, cols, n)
+        assert h.stats()["wide_tiles"] == tiles
+        h.run()
+        a = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"]).copy()
+        h.run()
+        b = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"])
+    finally:
+        h.close()
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    assert np.array_equal(a, Cref) and np.array_equal(b, Cref)
+
+
+def test_wide_items_are_chosen_for_er_like_lists_only(oracle, lib):
+    """n_hint between 2 and 6 tile widths: block-rows sharing few column blocks (ER, 10 % block density) get
+    wide items, dense lists (many members per column block) keep one tile per item; from 6 widths on every
+    bf16 / fp16 handle gets two tiles; tf32 chains that need fold passes keep one.  Real operands: within
+    the usual tolerances."""
+    rng = np.random.default_rng(77)
+    er = random_vbr(rng, 64, 4096, 64, [64] * 64, 0.1, values="real")
+    dense = random_vbr(rng, 16, 1024, 64, [64] * 16, 0.9, values="real")
+    n = 1024
+    for v, cols, expect in ((er, 4096, 2), (dense, 1024, 1)):
+        Bm = rng.standard_normal((n, cols)).astype(np.float32)
+        h = sparta_b200.Handle.from_vbr(v["rows"], cols, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                        precision="bf16", n_hint=n)
+        try:
+            assert h.stats()["wide_tiles"] == expect
+            h.set_B(Bm, cols, n)
+            h.run()
+            Cg = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"])
+        finally:
+            h.close()
+        Cr = oracle.vbr_multiply(rounded(v, "bf16"), round_to(Bm, "bf16"), n)
+        assert rel_err(Cg, Cr) <= TOL_ROUNDED
+    h = sparta_b200.Handle.from_vbr(er["rows"], 4096, 64, er["row_part"], er["nzcount"], er["jab"], er["mab"],
+                                    precision="bf16", n_hint=256)
+    try:
+        assert h.stats()["wide_tiles"] == 1       # n spans one tile: nothing to share
+    finally:
+        h.close()
+    for precision, chain, expect in (("bf16", 0, 2), ("tf32", 64, 1)):   # chains cut at 64 MMAs need the master accumulators
+        h = sparta_b200.Handle.from_vbr(dense["rows"], 1024, 64, dense["row_part"], dense["nzcount"], dense["jab"],
+                                        dense["mab"], precision=precision, n_hint=2048, max_chain=chain)
+        try:
+            assert h.stats()["wide_tiles"] == expect
+        finally:
+            h.close()
+
+
+def test_wide_items_split_accumulate_and_row_major(oracle, lib):
+    """Wide items cut into split pieces (red.add into tiles zeroed in-kernel: T x 128-column pieces per CTA),
+    with beta = 1 and with a row-major C."""
+    rng = np.random.default_rng(43)
+    heights = [64] * 6
+    v = random_vbr(rng, len(heights), 8192, 64, heights, 0.3, values="int")
+    n = 1000
+    Bm = rng.integers(-3, 4, size=(n, 8192)).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    for tiles in (2, 4):
+        h = sparta_b200.Handle.from_vbr(v["rows"], 8192, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                        precision="bf16", split_k=2, wide_tiles=tiles)
+        try:
+            h.set_B(Bm, 8192, n)
+            st = h.stats()
+            assert st["split_pieces"] > 0 and st["zero_tiles"] > 0 and st["wide_tiles"] == tiles
+            h.run()
+            a = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"]).copy()
+            h.run()
+            b = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"])
+        finally:
+            h.close()
+        assert np.array_equal(a, Cref) and np.array_equal(b, Cref)
+
+
 @pytest.mark.parametrize("mode", ["single", "pair"])
 @pytest.mark.parametrize("precision,max_chain", [("bf16", 0), ("fp16", 0), ("tf32", 24), ("tf32", 0)])
 def test_split_pieces_bit_exact(oracle, lib, precision, max_chain, mode):
