@@ -593,6 +593,7 @@ def run_ours(args, wl):
                       "sched_imbalance": st["sched_imbalance"], "grid": st["grid"], "items": st["items"],
                       "team": st["team"], "split_pieces": st["split_pieces"], "zero_tiles": st["zero_tiles"],
                       "gather_rows": st["gather_rows"], "gather_nnz": st["gather_nnz"], "chunks": st["chunks"],
+                      "wide_tiles": st["wide_tiles"], "super_rows": st["super_rows"], "smem_bytes": st["smem_bytes"],
                       "shard_block_rows": [int(c) for c in cuts], "per_rank_ms_per_step": per_rank_ms,
                       "rebalanced_from": rebalance},
         }
@@ -779,8 +780,11 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_r
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    each = []
     for _ in range(steps):
+        ts = time.perf_counter()
         once()
+        each.append(1e3 * (time.perf_counter() - ts))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -802,7 +806,8 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_r
     # nonzeros actually sent: this rank's (offset, value) pairs; the index arrays are host-side input
     out = {"value": total_flops * steps / sec / 1e12, "unit": "TFLOP/s",
            "h2d_bytes_per_step": int(h2d_b + len(colind) * 12 + 0), "d2h_bytes_per_step": int(d2h), "steps": steps,
-           "ms_per_step": 1e3 * sec / steps, "max_rel_diff_vs_resident_handle": diff,
+           "ms_per_step": 1e3 * sec / steps, "ms_each_step_this_rank": [round(x, 2) for x in each],
+           "max_rel_diff_vs_resident_handle": diff,
            "same_result": bool(diff <= 1e-6), "host_input_bytes": int(h2d + Bm.nbytes if rank == 0 else h2d),
            "call": ("sparta_csr_vbr_spmm (host CSR + grouping + host B -> host C: index build, nonzeros and B up, "
                     "device-side block rebuild + pack, kernel, C down; pinned host buffers; wall clock)" if world == 1 else
@@ -854,7 +859,7 @@ def main():
                     help="operand precision (default: the workload's, bf16 unless BASELINE names another)")
     ap.add_argument("--weighted", action="store_true", help="uniform(-1,1) values instead of the pattern-only matrix")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e-vbr", action="store_true", help="skip the extra timing of the sparta_vbr_spmm call on host VBR arrays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-c", action="store_true", help="multi-GPU: also all-gather C over NCCL and verify it")

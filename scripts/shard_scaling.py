@@ -46,7 +46,7 @@ def main():
         for r in range(world):
             h = sparta_b200.Handle.from_vbr(v["rows"], v["cols"], wl["w"], v["row_part"], v["nzcount"], v["jab"],
                                             v["mab"], precision=args.precision, block_row_begin=int(cuts[r]),
-                                            block_row_end=int(cuts[r + 1]), split_k=split, **extra)
+                                            block_row_end=int(cuts[r + 1]), split_k=split, n_hint=n, **extra)
             h.set_B_device(Bd.data_ptr(), v["cols"], n)
             st = h.stats()
             stream = torch.cuda.ExternalStream(h.stream)

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/sparta_b200.h"
@@ -94,6 +95,79 @@ static void dev_free(T*& p, cudaStream_t s) {
   p = nullptr;
 }
 
+// ---- pinned host staging, cached like the device pool ------------------------------------------
+// What the library itself builds on the host and sends up (the nonzeros of a CSR-built handle, the
+// schedule arrays, the pack jobs: ~60 MB for BASELINE config #3) used to leave from pageable memory:
+// the driver stages such copies through its own bounce buffer at a few GB/s and the call blocks until
+// the stream reaches it.  Blocks of page-locked memory are kept in a process-wide free list (first use
+// pays cudaHostAlloc, like the device pool pays cudaMalloc); sparta_release_workspace() frees them.
+struct PinnedCache {
+  std::mutex m;
+  std::vector<std::pair<void*, size_t>> free_list;
+  std::unordered_map<void*, size_t> live;
+};
+static PinnedCache& pinned_cache() {
+  static PinnedCache* c = new PinnedCache();   // never destroyed: handles may outlive static destructors
+  return *c;
+}
+static void* pinned_acquire(size_t bytes) {
+  if (getenv("SPARTA_PAGEABLE_STAGING")) return nullptr;
+  size_t want = size_t{1} << 16;
+  while (want < bytes) want <<= 1;
+  if (want > (size_t{1} << 24)) want = (bytes + (size_t{1} << 24) - 1) >> 24 << 24;   // 16 MB steps above 16 MB
+  PinnedCache& c = pinned_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.m);
+    size_t best = c.free_list.size();
+    for (size_t i = 0; i < c.free_list.size(); ++i)
+      if (c.free_list[i].second >= bytes && c.free_list[i].second <= 2 * want &&
+          (best == c.free_list.size() || c.free_list[i].second < c.free_list[best].second))
+        best = i;
+    if (best < c.free_list.size()) {
+      const auto blk = c.free_list[best];
+      c.free_list.erase(c.free_list.begin() + static_cast<std::ptrdiff_t>(best));
+      c.live[blk.first] = blk.second;
+      return blk.first;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(c.m);
+  c.live[p] = want;
+  return p;
+}
+static void pinned_release(void* p) {
+  if (!p) return;
+  PinnedCache& c = pinned_cache();
+  std::lock_guard<std::mutex> lock(c.m);
+  auto it = c.live.find(p);
+  if (it == c.live.end()) return;
+  c.free_list.emplace_back(p, it->second);
+  c.live.erase(it);
+}
+static void pinned_trim() {
+  PinnedCache& c = pinned_cache();
+  std::vector<std::pair<void*, size_t>> blocks;
+  {
+    std::lock_guard<std::mutex> lock(c.m);
+    blocks.swap(c.free_list);
+  }
+  for (auto& b : blocks) cudaFreeHost(b.first);
+  cudaGetLastError();
+}
+// RawBuf hooks (host_formats.h): page-locked when the cache can supply it, else the C heap
+static void* pinned_or_malloc(size_t bytes, bool* pinned) {
+  void* p = pinned_acquire(bytes);
+  *pinned = p != nullptr;
+  return p ? p : malloc(bytes ? bytes : 1);
+}
+static void pinned_or_free(void* p, bool pinned) {
+  if (pinned) pinned_release(p); else free(p);
+}
+
 struct sparta_host_vbr { HostVBR v; };
 struct sparta_host_bell { HostBell b; };
 
@@ -106,6 +180,7 @@ struct sparta_plan {
 };
 
 struct sparta_handle {
+  std::vector<void*> staged;   // pinned blocks the stream may still be reading (released after a synchronisation)
   int device = 0;
   int kind = 0;   // 0: block-sparse (VBR / Blocked-ELL) on the tcgen05 kernel, 1: CSR gather kernel
   cudaStream_t stream = nullptr;
@@ -566,6 +641,7 @@ static const char* build_structure_choosing_tiles(const BlockRows& view, const s
 
 // ---- handle construction ---------------------------------------------------
 
+static void release_staged(sparta_handle* h);
 static void free_handle(sparta_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
@@ -578,6 +654,7 @@ static void free_handle(sparta_handle* h) {
     for (auto& gp : h->gather_passes) { dev_free(gp.beg, s); dev_free(gp.end, s); dev_free(gp.order, s); }
     cudaStreamSynchronize(s);   // the blocks are back in the pool before the stream goes away
   }
+  release_staged(h);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->up0) cudaEventDestroy(h->up0);
@@ -586,12 +663,28 @@ static void free_handle(sparta_handle* h) {
   delete h;
 }
 
+// Host array -> device through a pinned block of the handle when it is large enough to matter (small
+// pageable copies are embedded in the command stream and do not block either).
+static cudaError_t staged_copy(sparta_handle* h, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  void* pin = bytes > (size_t{1} << 16) ? pinned_acquire(bytes) : nullptr;
+  if (pin) {
+    memcpy(pin, src, bytes);
+    h->staged.push_back(pin);
+    src = pin;
+  }
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+}
+// after a stream synchronisation: nothing reads the handle's staging blocks any more
+static void release_staged(sparta_handle* h) {
+  for (void* p : h->staged) pinned_release(p);
+  h->staged.clear();
+}
 template <class T>
-static cudaError_t upload_vec(const std::vector<T>& v, T** dptr, cudaStream_t s) {
-  cudaError_t e = dev_alloc(dptr, v.size() * sizeof(T), s);
+static cudaError_t upload_vec(const std::vector<T>& v, T** dptr, sparta_handle* h) {
+  cudaError_t e = dev_alloc(dptr, v.size() * sizeof(T), h->stream);
   if (e != cudaSuccess) return e;
-  if (!v.empty()) e = cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-  return e;
+  return staged_copy(h, *dptr, v.data(), v.size() * sizeof(T));
 }
 
 // Device, stream and events of a new handle.  Returns SPARTA_OK or a failure code (handle freed).
@@ -869,10 +962,10 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   }
   h->rows = h->st.rows;
   pick_pipeline(h->st.max_chunk_bytes, o, h->st.tiles, &h->panel_stages, &h->a_ring_bytes, &h->a_slot_bytes, &h->producers);
-  H_TRY(upload_vec(h->st.segs, &h->d_segs, h->stream));
-  H_TRY(upload_vec(h->st.srows, &h->d_srows, h->stream));
-  H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h->stream));
-  H_TRY(upload_vec(h->st.tables, &h->d_tables, h->stream));
+  H_TRY(upload_vec(h->st.segs, &h->d_segs, h));
+  H_TRY(upload_vec(h->st.srows, &h->d_srows, h));
+  H_TRY(upload_vec(h->st.chunks, &h->d_chunks, h));
+  H_TRY(upload_vec(h->st.tables, &h->d_tables, h));
   H_TRY(dev_alloc(&h->d_a, h->st.a_bytes, h->stream));
   if (h->st.sparse_images && h->st.a_bytes) H_TRY(cudaMemsetAsync(h->d_a, 0, h->st.a_bytes, h->stream));
   if (h->st.n_jobs > 0) {
@@ -880,7 +973,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
     size_t at = 0;
     for (const auto& part : h->st.job_parts) {
       if (part.empty()) continue;
-      H_TRY(cudaMemcpyAsync(d_jobs + at, part.data(), part.size() * sizeof(PackJob), cudaMemcpyHostToDevice, h->stream));
+      H_TRY(staged_copy(h, d_jobs + at, part.data(), part.size() * sizeof(PackJob)));
       at += part.size();
     }
     H_TRY(pack_a_images(d_src, d_jobs, h->st.n_jobs, h->d_a, o.precision, h->stream, static_cast<int64_t>(h->st.a_bytes)));
@@ -890,7 +983,10 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   std::vector<std::vector<PackJob>>().swap(h->st.job_parts);   // pageable copies are staged before cudaMemcpyAsync returns
   H_TRY(cudaEventRecord(h->up1, h->stream));
   // The public create returns only when the caller's arrays are no longer being read.
-  if (!defer_sync) H_TRY(cudaStreamSynchronize(h->stream));
+  if (!defer_sync) {
+    H_TRY(cudaStreamSynchronize(h->stream));
+    release_staged(h);
+  }
   if (timing)
     fprintf(stderr, "sparta create: host schedule + enqueue of the A upload (%s) %.1f ms, enqueue of the rest %.1f ms\n",
             sparse_upload ? "nonzeros only" : "dense",
@@ -922,20 +1018,21 @@ int sparta_device_count(void) {
 // Uploads the gather rows of a hybrid handle (values rounded to the operand precision on the device).
 // On failure the handle is freed.
 static int attach_gather(sparta_handle* h, const GatherPart& gp, int precision) {
-  cudaError_t e = upload_vec(gp.colind, &h->d_colind, h->stream);
-  if (e == cudaSuccess) e = upload_vec(gp.val, &h->d_val, h->stream);
+  cudaError_t e = upload_vec(gp.colind, &h->d_colind, h);
+  if (e == cudaSuccess) e = upload_vec(gp.val, &h->d_val, h);
   h->gather_passes.assign(gp.passes.size(), sparta_handle::GatherPassDev());
   for (size_t pi = 0; pi < gp.passes.size() && e == cudaSuccess; ++pi) {
     sparta_handle::GatherPassDev& d = h->gather_passes[pi];
-    e = upload_vec(gp.passes[pi].beg, &d.beg, h->stream);
-    if (e == cudaSuccess) e = upload_vec(gp.passes[pi].end, &d.end, h->stream);
-    if (e == cudaSuccess) e = upload_vec(gp.passes[pi].order, &d.order, h->stream);
+    e = upload_vec(gp.passes[pi].beg, &d.beg, h);
+    if (e == cudaSuccess) e = upload_vec(gp.passes[pi].end, &d.end, h);
+    if (e == cudaSuccess) e = upload_vec(gp.passes[pi].order, &d.order, h);
     d.work = static_cast<int64_t>(gp.passes[pi].order.size());
     d.heavy = gp.passes[pi].heavy;
   }
   if (e == cudaSuccess) e = round_values(h->d_val, static_cast<int64_t>(gp.val.size()), precision, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // the host vectors go away
   if (e != cudaSuccess) { free_handle(h); return fail_cuda(e, "upload of the gather rows"); }
+  release_staged(h);
   h->gather_rows = gp.rows;
   h->gather_work = gp.passes.empty() ? 0 : static_cast<int64_t>(gp.passes[0].order.size());
   h->nnz = static_cast<int64_t>(gp.val.size());
@@ -963,6 +1060,9 @@ static int vbr_create_from_csr_impl(sparta_handle** out, int64_t rows, int64_t c
   unsigned hw = std::thread::hardware_concurrency();
   const int threads = static_cast<int>(std::max(1u, std::min(hw ? hw : 8u, 32u)));
   HostVBRSparse hv;
+  // the nonzero lists are written by the filling threads straight into page-locked memory: they cross PCIe by DMA
+  hv.nz_off.acquire_fn = pinned_or_malloc; hv.nz_off.release_fn = pinned_or_free;
+  hv.nz_val.acquire_fn = pinned_or_malloc; hv.nz_val.release_fn = pinned_or_free;
   const char* e = host_vbr_fill_sparse(rows, cols, rowptr, colind, val, val == nullptr, grouping, block_col_size,
                                        row_block_size, force_fixed_size != 0, threads, &hv);
   if (*e) return fail(SPARTA_ERR_INVALID, e);
@@ -1050,10 +1150,16 @@ static int vbr_create_from_csr_impl(sparta_handle** out, int64_t rows, int64_t c
     }
     pre.total = static_cast<int64_t>(pre.idx[0].size());
   }
-  const int rc = create_common(out, hybrid ? tall : br, nullptr, src_hi - src_lo, ix.cols, o, 0, false, &pre);
+  // The one-shot callers defer the synchronisation: pageable lists are staged by the driver before the copy
+  // call returns, page-locked ones (the spans) are handed to the handle, which releases them after its next
+  // synchronisation.
+  const int rc = create_common(out, hybrid ? tall : br, nullptr, src_hi - src_lo, ix.cols, o, 0, defer_sync, &pre);
   if (rc != SPARTA_OK) return rc;
-  (void)defer_sync;   // the nonzero lists above are locals: the upload is complete when this returns
   sparta_handle* h = *out;
+  if (defer_sync && pre.span_idx) {
+    if (hv.nz_off.tag) { h->staged.push_back(hv.nz_off.p); hv.nz_off.p = nullptr; }
+    if (hv.nz_val.tag) { h->staged.push_back(hv.nz_val.p); hv.nz_val.p = nullptr; }
+  }
   h->rows = shard_rows;
   h->st.rows = shard_rows;
   h->block_rows = hi - lo;
@@ -1269,11 +1375,14 @@ static int csr_create_impl(sparta_handle** out, int64_t rows, int64_t cols, cons
   h->heavy_rows = 0;
   while (h->heavy_rows < nrows && ptr[order[h->heavy_rows] + 1] - ptr[order[h->heavy_rows]] > kCsrHeavyNnz)
     ++h->heavy_rows;
-  H_TRY(upload_vec(col32, &h->d_colind, h->stream));
-  H_TRY(upload_vec(ptr, &h->d_rowptr, h->stream));
-  H_TRY(upload_vec(order, &h->d_row_order, h->stream));
+  H_TRY(upload_vec(col32, &h->d_colind, h));
+  H_TRY(upload_vec(ptr, &h->d_rowptr, h));
+  H_TRY(upload_vec(order, &h->d_row_order, h));
   H_TRY(cudaEventRecord(h->up1, h->stream));
-  if (!defer_sync || !val) H_TRY(cudaStreamSynchronize(h->stream));
+  if (!defer_sync || !val) {
+    H_TRY(cudaStreamSynchronize(h->stream));
+    release_staged(h);
+  }
 #undef H_TRY
   *out = h;
   return SPARTA_OK;
@@ -1293,6 +1402,10 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
   if (h->kind == 1 && n > (1 << 30)) return fail(SPARTA_ERR_INVALID, "n too large");
   CU_TRY(cudaSetDevice(h->device));
   CU_TRY(cudaEventRecord(h->up0, h->stream));
+  const bool timing = getenv("SPARTA_TIMING") != nullptr;
+  const auto ts0 = std::chrono::steady_clock::now();
+  auto ts_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count(); };
+  double ts_conv = 0, ts_assign = 0;
   const int esize = (h->kind == 1 && h->sopt.precision == PREC_TF32) ? 4 : prec_esize(h->sopt.precision);
   // block kernel: [n][ldk] k-contiguous;  CSR kernel: [cols][ldn] n-contiguous, ldn = n rounded to 8
   const int64_t ldk = h->kind == 1 ? (n + 7) / 8 * 8 : (h->cols + 63) / 64 * 64;
@@ -1347,18 +1460,20 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
   }
   dev_free(d_stage, h->stream);
   if (e != cudaSuccess) return fail_cuda(e, "B conversion");
+  ts_conv = ts_ms();
 
   if (n != h->n) {
     if (h->kind == 0) {
       const char* serr = build_assignment(h->st, h->sopt, n, h->cols, &h->as);
       if (*serr) return fail(SPARTA_ERR_INVALID, serr);
+      ts_assign = ts_ms();
       dev_free(h->d_items, h->stream); dev_free(h->d_cta_ptr, h->stream); dev_free(h->d_cta_items, h->stream);
       dev_free(h->d_zero_jobs, h->stream);
       h->d_zero_jobs = nullptr;
-      if (!h->as.zero_jobs.empty()) CU_TRY(upload_vec(h->as.zero_jobs, &h->d_zero_jobs, h->stream));
-      CU_TRY(upload_vec(h->as.items, &h->d_items, h->stream));
-      CU_TRY(upload_vec(h->as.cta_ptr, &h->d_cta_ptr, h->stream));
-      CU_TRY(upload_vec(h->as.cta_items, &h->d_cta_items, h->stream));
+      if (!h->as.zero_jobs.empty()) CU_TRY(upload_vec(h->as.zero_jobs, &h->d_zero_jobs, h));
+      CU_TRY(upload_vec(h->as.items, &h->d_items, h));
+      CU_TRY(upload_vec(h->as.cta_ptr, &h->d_cta_ptr, h));
+      CU_TRY(upload_vec(h->as.cta_items, &h->d_cta_items, h));
     }
     // C: column-major ld padded to 4 rows so the epilogue can use 16-byte stores
     h->ldc = h->c_row_major ? n : (h->rows + 3) / 4 * 4;
@@ -1374,7 +1489,13 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
     h->n = n;
   }
   CU_TRY(cudaEventRecord(h->up1, h->stream));
-  if (!defer_sync) CU_TRY(cudaStreamSynchronize(h->stream));
+  if (timing)
+    fprintf(stderr, "sparta set_B: upload / conversion enqueued %.1f ms, work assignment %.1f, its upload + C %.1f\n", ts_conv,
+            ts_assign > 0 ? ts_assign - ts_conv : 0.0, ts_ms() - (ts_assign > 0 ? ts_assign : ts_conv));
+  if (!defer_sync) {
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    release_staged(h);
+  }
   return SPARTA_OK;
 }
 
@@ -1580,6 +1701,7 @@ int sparta_synchronize(sparta_handle* h) {
   if (!h) return fail(SPARTA_ERR_INVALID, "NULL handle");
   CU_TRY(cudaSetDevice(h->device));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  release_staged(h);
   return SPARTA_OK;
 }
 
@@ -1846,6 +1968,7 @@ int sparta_release_workspace(void) {
   }
   cudaSetDevice(cur);
   cudaGetLastError();
+  pinned_trim();
   return SPARTA_OK;
 }
 

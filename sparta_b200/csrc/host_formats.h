@@ -40,14 +40,24 @@ template <class T>
 struct RawBuf {                  // uninitialised storage: the filling threads touch the pages first
   T* p = nullptr;
   size_t n = 0;
+  // optional allocator of the owner (the C ABI layer hands out page-locked blocks so that the arrays can
+  // cross PCIe by DMA straight from where the threads wrote them); tag is returned to release_fn
+  void* (*acquire_fn)(size_t bytes, bool* tag) = nullptr;
+  void (*release_fn)(void* p, bool tag) = nullptr;
+  bool tag = false;
   RawBuf() = default;
   RawBuf(const RawBuf&) = delete;
   RawBuf& operator=(const RawBuf&) = delete;
-  ~RawBuf() { free(p); }
+  ~RawBuf() { drop(); }
+  void drop() {
+    if (p) { if (release_fn) release_fn(p, tag); else free(p); }
+    p = nullptr;
+  }
   bool alloc(size_t count) {
-    free(p);
+    drop();
     n = count;
-    p = static_cast<T*>(malloc((count ? count : 1) * sizeof(T)));
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    p = static_cast<T*>(acquire_fn ? acquire_fn(bytes, &tag) : malloc(bytes));
     return p != nullptr;
   }
   T& operator[](size_t i) { return p[i]; }
