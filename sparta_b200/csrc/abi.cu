@@ -180,6 +180,9 @@ struct sparta_plan {
 };
 
 struct sparta_handle {
+  bool chain_ok = false;       // the last kernel enqueued on the stream is this handle's own SpMM launch and nothing
+                               // it reads before its epilogue has changed since (cleared by set_B): the next launch
+                               // may overlap its tail (spmm_launch, overlap_previous)
   std::vector<void*> staged;   // pinned blocks the stream may still be reading (released after a synchronisation)
   int device = 0;
   int kind = 0;   // 0: block-sparse (VBR / Blocked-ELL) on the tcgen05 kernel, 1: CSR gather kernel
@@ -1401,6 +1404,7 @@ static int set_b_impl(sparta_handle* h, const float* B, int64_t ld, int64_t n, i
   if (ld < min_ld) return fail(SPARTA_ERR_INVALID, "leading dimension of B too small");
   if (h->kind == 1 && n > (1 << 30)) return fail(SPARTA_ERR_INVALID, "n too large");
   CU_TRY(cudaSetDevice(h->device));
+  h->chain_ok = false;   // B, the work assignment and C's buffer change below
   CU_TRY(cudaEventRecord(h->up0, h->stream));
   const bool timing = getenv("SPARTA_TIMING") != nullptr;
   const auto ts0 = std::chrono::steady_clock::now();
@@ -1666,11 +1670,22 @@ static int launch(sparta_handle* h, unsigned long long* trace = nullptr, int tra
     p.sync_counter = h->d_sync;
     p.sync_target = h->sync_total;
   }
-  cudaError_t e = spmm_launch(p, h->d_B, h->cols, h->ldk, h->sopt.precision, h->as.grid, h->stream, &err);
+  // Back-to-back multiplies of one handle are chained with programmatic dependent launch.  Measured
+  // (profiles/r2_pdl.md): letting a whole item's MMAs overlap the previous grid's tail (mode 1) helps
+  // mid-size shards (a quarter of config #3: 0.860 -> 0.790 ms) but costs config #3 itself 15 % -- the
+  // workers of a team start out of step and re-fetch their A images; overlapping only the launch, the
+  // prologue and the first stages' copies (mode 2, the default) is 2-4 % faster everywhere tried.
+  // SPARTA_PDL_MODE = 0 / 1 / 2 overrides.
+  static const int chain_mode = getenv("SPARTA_PDL_MODE") ? atoi(getenv("SPARTA_PDL_MODE")) : 2;
+  const bool chain = h->chain_ok && chain_mode > 0 && trace == nullptr && h->gather_work == 0;
+  p.chain_wait_mma = chain_mode != 1;
+  cudaError_t e = spmm_launch(p, h->d_B, h->cols, h->ldk, h->sopt.precision, h->as.grid, h->stream, &err, chain);
   if (e != cudaSuccess) {
     if (p.n_zero_jobs) h->sync_total -= static_cast<unsigned long long>(h->as.grid);   // nothing ran
+    h->chain_ok = false;
     return fail_cuda(e, err);
   }
+  h->chain_ok = trace == nullptr;
   ++h->launches;
   return SPARTA_OK;
 }

@@ -360,6 +360,11 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // Programmatic dependent launch (back-to-back multiplies of one handle): the next launch's CTAs may take
+  // an SM as soon as this grid's CTA leaves it, and run their copies and MMAs (reads of A, B and the
+  // schedule only) while the slowest CTAs of this grid finish; their epilogue warps wait for this grid
+  // to complete (griddepcontrol.wait below) before the first write to C.  No-ops in an ordinary launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int it_begin = p.cta_ptr[worker];
   const int it_end = p.cta_ptr[worker + 1];
@@ -539,6 +544,9 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
       uint32_t use = 0, slot = 0, phase = 0;
       uint32_t acc_use[2] = {0, 0};
       int local = 0;
+      // chained launches, prefetch-only flavour: the copies of the first stages run ahead, the MMAs start
+      // together once the previous grid is done (the workers of a team stay in step on their A images)
+      if (p.chain_wait_mma) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int it = it_begin; it < it_end; ++it, ++local) {
         const Item item = load_item(p, it);
         const int chunk_count = static_cast<int>(item.count & kItemCountMask);
@@ -626,6 +634,8 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
     }
     uint32_t acc_use[2] = {0, 0};
     int local = 0;
+    // everything below writes (or, with accumulate, reads) C: the previous grid on the stream must be done
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool c_aligned = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
     bool zero_seen = p.n_zero_jobs == 0;
     if (p.n_zero_jobs > 0) {
@@ -910,7 +920,7 @@ cudaError_t spmm_max_coresident_ctas(int pair, int kind_tf32, int slots, int sme
 }
 
 cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total, int64_t ldk,
-                        int precision, int grid, cudaStream_t stream, const char** err) {
+                        int precision, int grid, cudaStream_t stream, const char** err, bool overlap_previous) {
   *err = "";
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
@@ -964,13 +974,19 @@ cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
   cfg.blockDim = dim3(p.producers == 2 ? kSpmmThreads : kSpmmThreads - 32, 1, 1);   // warp 6 exists only as a producer
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.pair ? 2 : 1;   // the two CTAs of a pair share one TPC
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (overlap_previous && p.trace == nullptr) {
+    // the kernel before this one on the stream is the same handle's previous multiply (see the kernel prologue)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   e = cudaLaunchKernelEx(&cfg, fn, tmap, p);
   if (e != cudaSuccess) { *err = "spmm kernel launch"; return e; }
   e = cudaGetLastError();

@@ -30,6 +30,9 @@ struct SpmmParams {
   int32_t         a_slot_bytes; // > 0: fixed-slot pipeline, every stage owns this many bytes for its A images
                                 //      (a_ring_bytes = panel_stages * a_slot_bytes); 0: byte ring
   int32_t         producers;    // copy-issuing warps per CTA: 1, or 2 (fixed slots only; alternate chunks)
+  int32_t         chain_wait_mma; // launched with programmatic stream serialisation: 1 = the MMA warp waits for the
+                                // previous grid before its first MMA (only the first stages' copies overlap that
+                                // grid's tail), 0 = only the epilogue warps wait (a whole item's MMAs may overlap)
   int32_t         tiles;        // column tiles of B per work item (fixed slots only): every stage holds `tiles` B panels
                                 // for one set of A images; tile t accumulates in TMEM columns [t * 512 / tiles, ...)
   // Split pieces (kItemAtomic) add into C tiles that must start from zero.  Every CTA zeroes its
@@ -66,7 +69,10 @@ static inline int spmm_smem_bytes(int panel_stages, int a_ring_bytes, int tiles 
 // gets a static description on failure.
 cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
                         int64_t ldk, int precision, int grid, cudaStream_t stream,
-                        const char** err);
+                        const char** err, bool overlap_previous = false);
+// overlap_previous: launch with programmatic stream serialisation -- allowed only when the previous kernel on
+// the stream reads and writes nothing this launch reads before its epilogue (the same handle's previous
+// multiply: A, B and the schedule are read-only between set_B calls).
 
 // CTAs of the persistent grid that can be resident at the same time (see spmm_kernel.cu).
 cudaError_t spmm_max_coresident_ctas(int pair, int kind_tf32, int slots, int smem_bytes, int* out);

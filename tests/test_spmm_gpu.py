@@ -168,6 +168,54 @@ def test_accumulate_beta_one_and_idempotence(oracle, lib):
     h.close()
 
 
+@pytest.mark.parametrize("mode", ["single", "pair"])
+def test_back_to_back_launches_overlap_safely(oracle, lib, mode):
+    """Launches of one handle enqueued back to back are chained with programmatic dependent launch: the next
+    grid's copies and MMAs may start while the previous grid's slowest CTAs finish, its epilogue waits for
+    that grid (griddepcontrol.wait) before touching C.  Checked where an early write would show: split
+    pieces (tiles zeroed in-kernel, then red.add), beta = 1 (C is read back by the next launch), and a set_B
+    between two launches (B changes: the chain must be broken).  Integer operands: bit-exact."""
+    rng = np.random.default_rng(47)
+    heights = [64, 64, 64, 30, 64, 64, 64, 64, 64, 17, 64, 64, 1, 64]
+    v = random_vbr(rng, len(heights), 4096, 64, heights, 0.7, values="int")
+    n = 600
+    Bm = rng.integers(-3, 4, size=(n, 4096)).astype(np.float32)
+    Cref = oracle.vbr_multiply(v, Bm, n)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    split_k=2, gather_max_height=-1, n_hint=n, **MODES[mode])
+    try:
+        h.set_B(Bm, 4096, n)
+        assert h.stats()["split_pieces"] > 0
+        for _ in range(8):
+            h.run_async()
+        h.synchronize()
+        assert np.array_equal(h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"]), Cref)
+        # a new B between two launches, nothing synchronised in between
+        B2 = rng.integers(-3, 4, size=(n, 4096)).astype(np.float32)
+        h.run_async()
+        h.set_B(B2, 4096, n)
+        h.run_async()
+        h.run_async()
+        h.synchronize()
+        assert np.array_equal(h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"]), oracle.vbr_multiply(v, B2, n))
+    finally:
+        h.close()
+    # beta = 1: five chained launches add the product five times
+    C0 = rng.integers(-5, 6, size=(n, v["rows"])).astype(np.float32)
+    h = sparta_b200.Handle.from_vbr(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], v["mab"],
+                                    accumulate=1, gather_max_height=-1, n_hint=n, **MODES[mode])
+    try:
+        h.set_B(Bm, 4096, n)
+        h.set_C(C0, v["rows"])
+        for _ in range(5):
+            h.run_async()
+        h.synchronize()
+        out = h.get_C(np.zeros((n, v["rows"]), np.float32), v["rows"])
+    finally:
+        h.close()
+    assert np.array_equal(out, C0 + 5 * Cref)
+
+
 def test_padded_leading_dimensions(oracle, lib):
     rng = np.random.default_rng(7)
     v = random_vbr(rng, 5, 100, 16, [16, 5, 16, 16, 11], 0.7, values="int")
