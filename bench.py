@@ -759,13 +759,15 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_r
                                              int(fixed), L._ptr(a_B), v["cols"], n, L._ptr(a_C), max(rows_s, 1),
                                              L.PRECISIONS[args.precision], C.byref(dt)))
             return
+        # B first: its upload (rank 0) and the NCCL broadcast are enqueued, then every rank builds the handle of
+        # its shard on the host while B crosses PCIe and NVLink
+        if rank == 0:
+            Bd.copy_(k_B, non_blocking=True)          # the ONE upload of B
+        dist.broadcast(Bd, 0)                          # NCCL over NVLink (returns once enqueued)
         hh = sparta_b200.Handle.from_csr_grouping(N_rows, N_rows, a_rowptr, a_colind, a_val, a_grp, w, wl["rb"], fixed,
                                                   precision=args.precision, device=dev.index, block_row_begin=lo,
-                                                  block_row_end=hi, **tuning_opts(args))
+                                                  block_row_end=hi, n_hint=n, **tuning_opts(args))
         try:
-            if rank == 0:
-                Bd.copy_(k_B, non_blocking=True)          # the ONE upload of B
-            dist.broadcast(Bd, 0)                          # NCCL over NVLink
             torch.cuda.current_stream().synchronize()
             if rows_s:
                 hh.set_B_device(Bd.data_ptr(), v["cols"], n)
