@@ -798,6 +798,12 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_r
     h2d = a_rowptr.nbytes + a_colind.nbytes + a_grp.nbytes + (a_val.nbytes if a_val is not None else 0)
     h2d_b = Bm.nbytes if rank == 0 else 0
     d2h = rows_s * n * 4
+    each_all = [[round(x, 2) for x in each]]
+    if dist is not None:
+        et = torch.tensor(each, dtype=torch.float64, device=dev)
+        gathered = [torch.empty_like(et) for _ in range(world)]
+        dist.all_gather(gathered, et)
+        each_all = [[round(float(x), 2) for x in g.tolist()] for g in gathered]
     t_all = torch.tensor([sec, float(h2d_b), float(d2h), float(diff)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t_all.clone()
@@ -808,7 +814,7 @@ def run_e2e(args, wl, v, lo, hi, n, Bm, world, rank, dev, dist, total_flops, c_r
     # nonzeros actually sent: this rank's (offset, value) pairs; the index arrays are host-side input
     out = {"value": total_flops * steps / sec / 1e12, "unit": "TFLOP/s",
            "h2d_bytes_per_step": int(h2d_b + len(colind) * 12 + 0), "d2h_bytes_per_step": int(d2h), "steps": steps,
-           "ms_per_step": 1e3 * sec / steps, "ms_each_step_this_rank": [round(x, 2) for x in each],
+           "ms_per_step": 1e3 * sec / steps, "ms_each_step_per_rank": each_all,
            "max_rel_diff_vs_resident_handle": diff,
            "same_result": bool(diff <= 1e-6), "host_input_bytes": int(h2d + Bm.nbytes if rank == 0 else h2d),
            "call": ("sparta_csr_vbr_spmm (host CSR + grouping + host B -> host C: index build, nonzeros and B up, "

@@ -7,7 +7,7 @@ python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r2p_bench_n1.json").read().strip().splitlines()[-1])
 print("value", d["value"], "ms", d["ms_per_step"], "frac", d["roofline"]["frac"], "check", d["check"]["ok"], "wide", d["setup"].get("wide_tiles"))
-print("e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step_this_rank", "same_result")})
+print("e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step_per_rank", "same_result")})
 print("e2e vbr", d["e2e"].get("vbr_arrays"))
 PY
 timeout 900 python bench.py --no-cpu-baseline --workload er14_fixed > gpurun_out/r2p_bench_er14.json 2>/dev/null
@@ -16,5 +16,5 @@ python - <<'PY'
 import json
 for f in ("er14", "a4"):
     d = json.loads(open(f"gpurun_out/r2p_bench_{f}.json").read().strip().splitlines()[-1])
-    print(f, "ms", d["ms_per_step"], d["value"], "check", d["check"]["ok"], "e2e", d["e2e"]["ms_per_step"], d["e2e"]["ms_each_step_this_rank"], d["e2e"]["same_result"])
+    print(f, "ms", d["ms_per_step"], d["value"], "check", d["check"]["ok"], "e2e", d["e2e"]["ms_per_step"], d["e2e"]["ms_each_step_per_rank"], d["e2e"]["same_result"])
 PY

@@ -19,7 +19,7 @@ if not lines:
 d = json.loads(lines[-1])
 e = d.get("e2e") or {}
 print(f"{d['config']['workload']} N={d['n_gpus']} value {d['value']:.1f} TFLOP/s {d['ms_per_step']:.4f} ms frac {d['roofline']['frac']:.3f} hbm_frac {d['roofline']['hbm_frac_of_measured']:.3f} check {d['check']}")
-print("  e2e", {k: e.get(k) for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "same_result")})
+print("  e2e", {k: e.get(k) for k in ("value", "ms_per_step", "ms_each_step_per_rank", "same_result")})
 print("  setup", {k: d['setup'][k] for k in ("b_broadcast_s", "grid", "items", "gather_rows", "gather_nnz", "shard_block_rows")})
 PY
   i=$((i+1))

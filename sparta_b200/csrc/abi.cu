@@ -112,23 +112,23 @@ static PinnedCache& pinned_cache() {
 }
 static void* pinned_acquire(size_t bytes) {
   if (getenv("SPARTA_PAGEABLE_STAGING")) return nullptr;
+  // size classes: powers of two from 64 KB to 64 MB, multiples of 64 MB above.  A request is served only by a
+  // block of ITS class, so a call that repeats (the one-shot routines) finds every block it used the last time
+  // whatever order its requests come in -- cudaHostAlloc synchronises the device and costs milliseconds
+  // (hundreds with several processes on the box), it must not recur.
   size_t want = size_t{1} << 16;
-  while (want < bytes) want <<= 1;
-  if (want > (size_t{1} << 24)) want = (bytes + (size_t{1} << 24) - 1) >> 24 << 24;   // 16 MB steps above 16 MB
+  while (want < bytes && want < (size_t{1} << 26)) want <<= 1;
+  if (want < bytes) want = (bytes + (size_t{1} << 26) - 1) >> 26 << 26;
   PinnedCache& c = pinned_cache();
   {
     std::lock_guard<std::mutex> lock(c.m);
-    size_t best = c.free_list.size();
     for (size_t i = 0; i < c.free_list.size(); ++i)
-      if (c.free_list[i].second >= bytes && c.free_list[i].second <= 2 * want &&
-          (best == c.free_list.size() || c.free_list[i].second < c.free_list[best].second))
-        best = i;
-    if (best < c.free_list.size()) {
-      const auto blk = c.free_list[best];
-      c.free_list.erase(c.free_list.begin() + static_cast<std::ptrdiff_t>(best));
-      c.live[blk.first] = blk.second;
-      return blk.first;
-    }
+      if (c.free_list[i].second == want) {
+        const auto blk = c.free_list[i];
+        c.free_list.erase(c.free_list.begin() + static_cast<std::ptrdiff_t>(i));
+        c.live[blk.first] = blk.second;
+        return blk.first;
+      }
   }
   void* p = nullptr;
   if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
@@ -519,8 +519,7 @@ static bool split_short_block_rows(const BlockRows& br, int max_height, const fl
     }
   }
   // nonzeros of the short block-rows, scanned by all host threads over contiguous ranges of them
-  unsigned hw = std::thread::hardware_concurrency();
-  const int T = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::min(hw ? hw : 8u, 32u), shorts.size() / 64 + 1)));
+  const int T = static_cast<int>(std::max<size_t>(1, std::min<size_t>(host_thread_budget(32), shorts.size() / 64 + 1)));
   std::vector<std::vector<int32_t>> t_col(T);
   std::vector<std::vector<float>> t_val(T);
   std::vector<int64_t> row_nnz(static_cast<size_t>(total_rows), 0);
@@ -726,9 +725,11 @@ struct SparseSource {
   std::vector<std::vector<int64_t>> idx;   // per scanning thread: element offsets of the nonzeros
   std::vector<std::vector<float>> val;
   int64_t total = 0;
-  // or one caller-owned span (offsets already relative to the source range)
+  // or one caller-owned span; its offsets count from element `base` of the whole source (a shard's lists are
+  // a slice of the matrix's lists: the scatter subtracts the shard's first element instead of the host)
   const int64_t* span_idx = nullptr;
   const float* span_val = nullptr;
+  int64_t base = 0;
 };
 
 // fraction of nonzero elements in ~256 K sampled elements (4096 windows of 64)
@@ -748,8 +749,7 @@ static double sampled_density(const float* src, int64_t n) {
 // All host threads scan disjoint ranges; gives up (returns false) as soon as the source turns
 // out denser than the sample suggested (12 bytes per nonzero against 4 per element).
 static bool scan_nonzeros(const float* src, int64_t n, SparseSource* out) {
-  unsigned hw = std::thread::hardware_concurrency();
-  const int T = static_cast<int>(std::max(1u, std::min(hw ? hw : 8u, 32u)));
+  const int T = host_thread_budget(32);
   out->idx.assign(T, {});
   out->val.assign(T, {});
   std::vector<char> gave_up(T, 0);
@@ -869,6 +869,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
   PackJob* d_jobs = nullptr;
   int64_t* d_idx = nullptr;   // nonzeros-only upload
   float* d_val = nullptr;
+  const auto tc_open = std::chrono::steady_clock::now();
   H_TRY(cudaEventRecord(h->up0, h->stream));
   bool sparse_upload = false;
   if (src_elems > 0) {
@@ -882,14 +883,21 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
     if (pre) {
       // the caller already holds the nonzeros (built from the CSR): only they cross PCIe
       sparse_upload = true;
+      auto mark = [&](const char* what) {
+        if (timing) fprintf(stderr, "  create mark %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
+      };
+      mark("d_src allocated");
       H_TRY(cudaMemsetAsync(d_src, 0, static_cast<size_t>(src_elems) * sizeof(float), h->stream));
+      mark("memset enqueued");
       if (pre->total > 0) {
         H_TRY(dev_alloc(&d_idx, static_cast<size_t>(pre->total) * sizeof(int64_t), h->stream));
         H_TRY(dev_alloc(&d_val, static_cast<size_t>(pre->total) * sizeof(float), h->stream));
+        mark("idx/val allocated");
         int64_t at = 0;
         if (pre->span_idx) {
           H_TRY(cudaMemcpyAsync(d_idx, pre->span_idx, static_cast<size_t>(pre->total) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
           H_TRY(cudaMemcpyAsync(d_val, pre->span_val, static_cast<size_t>(pre->total) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+          mark("copies enqueued");
         }
         for (size_t t = 0; t < pre->idx.size() && !pre->span_idx; ++t) {
           const size_t cnt = pre->idx[t].size();
@@ -898,7 +906,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
           H_TRY(cudaMemcpyAsync(d_val + at, pre->val[t].data(), cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
           at += static_cast<int64_t>(cnt);
         }
-        H_TRY(scatter_values(d_idx, d_val, pre->total, d_src, h->stream));
+        H_TRY(scatter_values(d_idx, d_val, pre->total, d_src - pre->base, h->stream));
         dev_free(d_idx, h->stream);
         dev_free(d_val, h->stream);
         d_idx = nullptr;
@@ -954,6 +962,7 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
                             cudaMemcpyHostToDevice, h->stream));
     }
   }
+  const auto tc_enq = std::chrono::steady_clock::now();
   sched.join();
   const auto tc1 = std::chrono::steady_clock::now();
   if (*serr || static_cast<int64_t>(h->st.max_chunk_bytes) > h->a_ring_bytes) {
@@ -991,7 +1000,10 @@ static int create_common(sparta_handle** out, BlockRows& br, const float* src_ho
     release_staged(h);
   }
   if (timing)
-    fprintf(stderr, "sparta create: host schedule + enqueue of the A upload (%s) %.1f ms, enqueue of the rest %.1f ms\n",
+    fprintf(stderr, "sparta create: [open %.1f, A upload enqueued %.1f, wait for the schedule %.1f] host schedule + enqueue of the A upload (%s) %.1f ms, enqueue of the rest %.1f ms\n",
+            std::chrono::duration<double, std::milli>(tc_open - tc0).count(),
+            std::chrono::duration<double, std::milli>(tc_enq - tc_open).count(),
+            std::chrono::duration<double, std::milli>(tc1 - tc_enq).count(),
             sparse_upload ? "nonzeros only" : "dense",
             std::chrono::duration<double, std::milli>(tc1 - tc0).count(),
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc1).count());
@@ -1060,8 +1072,7 @@ static int vbr_create_from_csr_impl(sparta_handle** out, int64_t rows, int64_t c
     return fail(SPARTA_ERR_INVALID, "invalid CSR input");
   sparta_options o;
   resolve_options(opt, &o);
-  unsigned hw = std::thread::hardware_concurrency();
-  const int threads = static_cast<int>(std::max(1u, std::min(hw ? hw : 8u, 32u)));
+  const int threads = host_thread_budget(32);
   HostVBRSparse hv;
   // the nonzero lists are written by the filling threads straight into page-locked memory: they cross PCIe by DMA
   hv.nz_off.acquire_fn = pinned_or_malloc; hv.nz_off.release_fn = pinned_or_free;
@@ -1134,11 +1145,12 @@ static int vbr_create_from_csr_impl(sparta_handle** out, int64_t rows, int64_t c
     }
   }
   SparseSource pre;
-  if (!hybrid && src_lo == 0) {
-    // the whole matrix (or a shard starting at block-row 0) without gather rows: the lists as they are
-    pre.span_idx = hv.nz_off.p;
-    pre.span_val = hv.nz_val.p;
-    pre.total = hv.nz_ptr[hi];
+  if (!hybrid) {
+    // the whole matrix or a shard of it without gather rows: the lists (a slice of them) as they are
+    pre.span_idx = hv.nz_off.p + hv.nz_ptr[lo];
+    pre.span_val = hv.nz_val.p + hv.nz_ptr[lo];
+    pre.total = hv.nz_ptr[hi] - hv.nz_ptr[lo];
+    pre.base = src_lo;
   } else {
     pre.idx.assign(1, {});
     pre.val.assign(1, {});

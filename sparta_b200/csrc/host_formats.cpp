@@ -4,6 +4,7 @@
 //   get_permutation / get_partition   src/general/utilities.cpp:8-43
 //   VBR::fill_from_CSR_inplace        src/general/vbr.cpp:135-237  (O(nnz*block_cols) there)
 //   prepare_cusparse_BLOCKEDELLPACK   src/cuda/cuda_utilities.cpp:1656-1710
+#include <sched.h>
 #include "host_formats.h"
 
 #include <stdio.h>
@@ -17,6 +18,43 @@
 #include <thread>
 
 namespace sparta {
+
+int host_thread_budget(int cap) {
+  static const int budget = [] {
+    if (const char* e = getenv("SPARTA_THREADS")) {
+      const int v = atoi(e);
+      if (v > 0) return v;
+    }
+    long n = 0;
+#ifdef __linux__
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+#endif
+    if (n <= 0) n = static_cast<long>(std::thread::hardware_concurrency());
+    if (n <= 0) n = 8;
+    // cgroup v2: "<quota> <period>" or "max <period>"; v1: two files
+    double quota = 0;
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      char q[64];
+      long period = 0;
+      if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) quota = atof(q) / period;
+      fclose(f);
+    } else {
+      long q = -1, period = 0;
+      if (FILE* fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(fq, "%ld", &q) != 1) q = -1; fclose(fq); }
+      if (FILE* fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(fp, "%ld", &period) != 1) period = 0; fclose(fp); }
+      if (q > 0 && period > 0) quota = static_cast<double>(q) / period;
+    }
+    if (quota >= 1.0 && quota < n) n = static_cast<long>(quota);
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+      const int w = atoi(e);
+      if (w > 1) n = std::max(1L, n / w);
+    }
+    return static_cast<int>(std::max(1L, n));
+  }();
+  return std::max(1, std::min(budget, cap));
+}
 
 // The reference orders rows with std::sort (unstable) keyed on the group id through a
 // comparator that takes `int` indices.  The order of rows inside a group is therefore

@@ -77,6 +77,12 @@ const char* host_vbr_fill_sparse(int64_t rows, int64_t cols, const int64_t* rowp
 const char* host_bellpack_from_vbr(int64_t rows, int64_t cols, int64_t bs, const int64_t* nzcount,
                                    const int64_t* jab, const float* mab, int threads, HostBell* out);
 
+// Host threads a call may start: the CPUs this process may run on (affinity mask), capped by the cgroup CPU
+// quota of the container (a process that runs more threads than its quota is throttled in 100 ms periods --
+// measured as 100 ms stalls inside cudaMemcpyAsync with two ranks on one box), divided by LOCAL_WORLD_SIZE
+// when a launcher that starts one process per GPU set it, overridden by SPARTA_THREADS; at most `cap`.
+int host_thread_budget(int cap);
+
 // ---- grouping cache -----------------------------------------------------------------------------
 // The reference can persist a grouping as `<outfile>.g`, one group id per line
 // (test/general/Matrix_Blocking.cpp:24-32, src/general/utilities.cpp:240-243), and reload it

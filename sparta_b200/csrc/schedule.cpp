@@ -4,6 +4,7 @@
 // jab_positions / mab_positions and the "nzs-th block of every block-row"
 // double loop of cublas_fixed_blocks_multiply (src/cuda/cuda_utilities.cpp:108-182)
 // and the per-level pointer arrays of cublas_blockmat_batched (:811-856).
+#include "host_formats.h"
 #include "schedule.h"
 
 #include <stdio.h>
@@ -348,8 +349,7 @@ static const char* build_structure_for(const BlockRows& br, const ScheduleOption
   const double t_groups = since();
   // ranges of super-rows balanced on block count, one per host thread
   const size_t n_groups = groups.size();
-  unsigned hw = std::thread::hardware_concurrency();
-  int T = static_cast<int>(std::max(1u, std::min(hw ? hw : 4u, 16u)));
+  int T = host_thread_budget(16);
   if (st.n_blocks < 20000 || n_groups < 8) T = 1;
   T = static_cast<int>(std::min<size_t>(T, std::max<size_t>(n_groups, 1)));
   std::vector<size_t> cut(T + 1, 0);
