@@ -194,6 +194,11 @@ def cpu_reference_sample(v, Bm, n, target_gflop, threads, variant=None, n_cols=N
         if flops[take].sum() >= target_gflop * 1e9 or len(take) == len(live):
             break
         want *= 2
+    # the smallest allowed sample is still too much CPU work at full n: the columns of B are independent in
+    # VBR::multiply (vbr.cpp:342-368), so the sample takes a leading subset of them (multiples of 64)
+    if n_cols is None and flops[take].sum() > 1.25 * target_gflop * 1e9:
+        nn = int(max(64, min(n, (n * target_gflop * 1e9 / flops[take].sum()) // 64 * 64)))
+        flops = 2.0 * area * nn
     jab_off = np.concatenate([[0], np.cumsum(nz)])
     mab_off = np.concatenate([[0], np.cumsum(area)])
     # the sample as `threads` small VBR matrices (block-rows dealt round-robin by descending work)
@@ -248,7 +253,11 @@ def run_reference_arm(args, wl):
     n = wl["n"]
     Bm = synth.seeded_B(v["cols"], n, seed=2)
     threads = args.cpu_threads or (os.cpu_count() or 1)
+    # every step is a bounded sample: sized so that warmup + steps end in about 2.5 minutes at the ~0.5 GFLOP/s
+    # a thread of this routine sustains when all cores run it (measured: 8.2 GFLOP/s on 16 threads)
     per_step = args.cpu_gflop_per_step
+    if per_step <= 0:
+        per_step = 0.5 * min(30.0, max(2.0, 150.0 / (args.warmup + args.steps)))
     times, flops, info = [], 0.0, None
     for i in range(args.warmup + args.steps):
         info = cpu_reference_sample(v, Bm, n, per_step * threads, threads)
@@ -565,7 +574,7 @@ def run_ours(args, wl):
                "sample": info["sample"] + f"; {info['seconds']:.1f} s", "host_cores_available": os.cpu_count()}
         # the reference's own optimisation levels on a smaller sample (the -O0 build is 8x slower)
         variants = {}
-        for var, cols_sub, gf in (("O0", 64, 0.5), ("O3", n, args.cpu_gflop / 4)):
+        for var, cols_sub, gf in (("O0", 64, 0.5), ("O3", None, args.cpu_gflop / 3)):
             from oracle.oracle_py import Reference
             if Reference.available(var):
                 vi = cpu_reference_sample(v, Bm, n, gf, 1, variant=var, n_cols=cols_sub)
@@ -892,9 +901,10 @@ def main():
     ap.add_argument("--no-e2e-vbr", action="store_true", help="skip the extra timing of the sparta_vbr_spmm call on host VBR arrays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-c", action="store_true", help="multi-GPU: also all-gather C over NCCL and verify it")
-    ap.add_argument("--cpu-gflop", type=float, default=40.0, help="size of the cpu_baseline sample")
-    ap.add_argument("--cpu-gflop-per-step", type=float, default=8.0,
-                    help="--impl reference: nonzero-block GFLOP per thread-step sample")
+    ap.add_argument("--cpu-gflop", type=float, default=24.0, help="size of the cpu_baseline sample (about 25 s of the reference's -O2 build)")
+    ap.add_argument("--cpu-gflop-per-step", type=float, default=0.0,
+                    help="--impl reference: nonzero-block GFLOP per thread and step (0: sized so that the run ends in "
+                         "about 2.5 minutes)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--rebalance", type=int, default=1,
                     help="multi-GPU: re-cut the modelled partition once with measured shard times when the slowest rank "

@@ -29,3 +29,4 @@ PY
 done
 timeout 900 python scripts/other_paths_time.py > gpurun_out/r2_other_entry_points.txt 2>&1; tail -6 gpurun_out/r2_other_entry_points.txt
 timeout 1200 python scripts/config5_sweep.py --out gpurun_out/r2_config5_sweep.json > gpurun_out/r2_config5_sweep.txt 2>&1; tail -4 gpurun_out/r2_config5_sweep.txt
+SKIP_TESTS=1 WORKLOADS="rmat16_a5:bf16" bash scripts/gpu_r2_ab.sh "--l2-slab-mb 80" "--l2-slab-mb 40" ""
