@@ -294,7 +294,11 @@ __device__ __forceinline__ Item load_item(const SpmmParams& p, int it) {
 //   chunk without sharing any state with the first.  Chosen when at least 3 such stages fit.
 // kSlots = false: the A images of the stages in flight share one byte ring (more stages in flight
 //   when chunk sizes vary a lot); single producer.
-template <bool kTf32, bool kPair, bool kSlots>
+// kWide = true (fixed slots only): a work item covers p.tiles (2 or 4) column tiles, every stage carries that many
+//   panels of B.  A separate instantiation because the loops over the tiles sit on the two tightest
+//   single-thread chains of the kernel (copy issue, MMA issue): with a run-time count of 1 they cost the
+//   one-tile schedules 3 % (bf16) to 9 % (tf32) -- measured, profiles/r2_wide_items.md.
+template <bool kTf32, bool kPair, bool kSlots, bool kWide>
 __global__ void __launch_bounds__(kSpmmThreads, 1)
 spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -304,7 +308,7 @@ spmm_vbr_sm100(const __grid_constant__ CUtensorMap tmap_b, const SpmmParams p) {
   uint8_t* smem = smem_raw + (base - raw_addr);
 
   const int P = p.panel_stages;
-  const int T = kSlots ? p.tiles : 1;                 // B panels per stage (column tiles per work item)
+  const int T = (kSlots && kWide) ? p.tiles : 1;      // B panels per stage (column tiles per work item)
   const uint32_t stage_panels = static_cast<uint32_t>(T) * kPanelBytes;
   const uint32_t panels = base;
   const uint32_t a_ring = base + P * stage_panels;
@@ -885,12 +889,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 typedef void (*KernelFn)(const CUtensorMap, const SpmmParams);
-static KernelFn pick_kernel(bool tf32, bool pair, bool slots) {
+static KernelFn pick_kernel(bool tf32, bool pair, bool slots, bool wide = false) {
+  if (slots && wide)
+    return tf32 ? (pair ? spmm_vbr_sm100<true, true, true, true> : spmm_vbr_sm100<true, false, true, true>)
+                : (pair ? spmm_vbr_sm100<false, true, true, true> : spmm_vbr_sm100<false, false, true, true>);
   if (slots)
-    return tf32 ? (pair ? spmm_vbr_sm100<true, true, true> : spmm_vbr_sm100<true, false, true>)
-                : (pair ? spmm_vbr_sm100<false, true, true> : spmm_vbr_sm100<false, false, true>);
-  return tf32 ? (pair ? spmm_vbr_sm100<true, true, false> : spmm_vbr_sm100<true, false, false>)
-              : (pair ? spmm_vbr_sm100<false, true, false> : spmm_vbr_sm100<false, false, false>);
+    return tf32 ? (pair ? spmm_vbr_sm100<true, true, true, false> : spmm_vbr_sm100<true, false, true, false>)
+                : (pair ? spmm_vbr_sm100<false, true, true, false> : spmm_vbr_sm100<false, false, true, false>);
+  return tf32 ? (pair ? spmm_vbr_sm100<true, true, false, false> : spmm_vbr_sm100<true, false, false, false>)
+              : (pair ? spmm_vbr_sm100<false, true, false, false> : spmm_vbr_sm100<false, false, false, false>);
 }
 
 // CTAs of the persistent grid the device can hold AT THE SAME TIME at this shared-memory
@@ -966,7 +973,7 @@ cudaError_t spmm_launch(const SpmmParams& p, const void* b_dev, int64_t k_total,
     *err = "two copy warps need the fixed-slot pipeline";
     return cudaErrorInvalidConfiguration;
   }
-  KernelFn fn = pick_kernel(p.kind_tf32 != 0, p.pair != 0, p.a_slot_bytes > 0);
+  KernelFn fn = pick_kernel(p.kind_tf32 != 0, p.pair != 0, p.a_slot_bytes > 0, tiles > 1);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(smem)"; return e; }
   cudaLaunchConfig_t cfg = {};
