@@ -31,10 +31,14 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <thread>
 #include <numeric>
 #include <set>
 #include <utility>
+#include <vector>
 
 #include "host_formats.h"
 
@@ -222,6 +226,94 @@ inline bool pruned(std::vector<float>& d, int64_t i, int64_t j, float tau) {
   return false;
 }
 
+// ---- speculative evaluation of a scan window on all host threads -----------------------------
+// The scans of -a 3 / -a 4 are sequential in their DECISIONS (a merge changes the pattern every later
+// distance is taken against) but merges are rare: one per ~20 000 comparisons on the R-MAT of BASELINE
+// config #4.  A window of upcoming candidates is therefore evaluated against the CURRENT pattern by all
+// threads (pure reads), then committed in order by one thread exactly like the sequential loop; at the
+// first merge the rest of the window is thrown away and re-evaluated against the new pattern.  Same
+// distances (same function, same operands), same order of decisions, same counters: the grouping is
+// identical by construction, and tests/test_blocking.py checks it against the reference build.
+class ScanPool {
+ public:
+  explicit ScanPool(int threads) : n_(std::max(1, threads)) {
+    for (int t = 1; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
+  }
+  ~ScanPool() {
+    stop_.store(true, std::memory_order_relaxed);
+    gen_.fetch_add(1, std::memory_order_release);
+    for (std::thread& w : workers_) w.join();
+  }
+  int threads() const { return n_; }
+  // fn(lo, hi) over contiguous slices of [0, count); returns when all slices are done
+  template <class F>
+  void run(int64_t count, const F& fn) {
+    if (n_ == 1 || count < 4 * n_) { fn(0, count); return; }
+    ctx_ = &fn;
+    call_ = [](const void* c, int64_t lo, int64_t hi) { (*static_cast<const F*>(c))(lo, hi); };
+    count_ = count;
+    pending_.store(n_ - 1, std::memory_order_relaxed);
+    gen_.fetch_add(1, std::memory_order_release);
+    fn(0, count / n_);
+    for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins)
+      if (spins > 2000) std::this_thread::yield();
+  }
+
+ private:
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) {
+        if (++spins > 4000) {
+          if (spins > 20000) std::this_thread::sleep_for(std::chrono::microseconds(50));
+          else std::this_thread::yield();
+        }
+      }
+      ++seen;
+      if (stop_.load(std::memory_order_relaxed)) return;
+      call_(ctx_, count_ * t / n_, count_ * (t + 1) / n_);
+      pending_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  const int n_;
+  std::vector<std::thread> workers_;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<int> pending_{0};
+  std::atomic<bool> stop_{false};
+  const void* ctx_ = nullptr;
+  void (*call_)(const void*, int64_t, int64_t) = nullptr;
+  int64_t count_ = 0;
+};
+
+struct Probe {
+  uint8_t state;   // 0: row already in a group, 1: pruned by the distances[] rule, 2: distance evaluated
+  float dist;
+};
+inline bool would_prune(const std::vector<float>& d, int64_t i, int64_t j, float tau) {
+  return d[i] != -1 && d[j] != -1 && std::abs(d[i] - d[j]) > tau;
+}
+// probes[t] for the candidates row_of(t), t in [0, count): pruning is tested BEFORE group membership,
+// like the sequential loops do (a pruned row has its distance reset even when it is already taken)
+template <class P, class RowOf>
+void probe_window(ScanPool& pool, const P& pat, int64_t gsize, int64_t i, float tau, const std::vector<float>& d,
+                  const int64_t* g, const RowOf& row_of, int64_t count, Probe* out) {
+  pool.run(count, [&](int64_t lo, int64_t hi) {
+    for (int64_t t = lo; t < hi; ++t) {
+      const int64_t j = row_of(t);
+      if (would_prune(d, i, j, tau)) { out[t].state = 1; continue; }
+      if (g[j] != -1) { out[t].state = 0; continue; }
+      out[t].state = 2;
+      out[t].dist = pat.dist(j, gsize);
+    }
+  });
+}
+constexpr int64_t kWindowMin = 2048, kWindowMax = 65536;
+// Half of the thread budget, at most 8: the windows are short (tens of microseconds of work), and with
+// every core spinning on the hand-over the scan got SLOWER than sequential on an 8-CPU container
+// (R-MAT 2^16, -a 4: 1 thread 50.1 s, 4 threads 20.1 s, 8 threads 55.3 s).
+inline int scan_threads() { return std::max(1, std::min(8, host_thread_budget(16) / 2)); }
+
 // -a 0, IterativeBlockingPattern (blocking.cpp:89-154): strict `<`; the pattern merge
 // runs whatever use_pattern says (the `if` at :128 guards only a timer macro).
 template <class P>
@@ -248,25 +340,38 @@ void run_iterative(const Rows& m, P& pat, float tau, bool use_size, int64_t* g, 
 template <class P>
 void run_clocked(const Rows& m, P& pat, float tau, bool use_size, bool use_pattern, int64_t* g, Acc& st) {
   std::vector<float> d = initial_distances(m.rows);
+  ScanPool pool(scan_threads());
+  std::vector<Probe> probes(static_cast<size_t>(kWindowMax));
   for (int64_t i = 0; i < m.rows; ++i) {
     if (g[i] != -1) continue;
     pat.seed(i);
     int64_t gsize = 1;
     g[i] = i;
-    for (int64_t j = i + 1; j < m.rows; ++j) {
-      if (pruned(d, i, j, tau)) continue;
-      if (g[j] != -1) continue;
-      ++st.comparisons;
-      const float dist = pat.dist(j, gsize);
-      d[j] = dist;
-      if (dist <= tau) {
-        st.merge_tau += dist;
-        st.row_distance += j - i;
-        ++st.merges;
-        g[j] = i;
-        if (use_pattern) pat.merge(j);
-        if (use_size) ++gsize;
+    int64_t window = kWindowMin;
+    for (int64_t j0 = i + 1; j0 < m.rows;) {
+      const int64_t count = std::min(window, m.rows - j0);
+      probe_window(pool, pat, gsize, i, tau, d, g, [j0](int64_t t) { return j0 + t; }, count, probes.data());
+      int64_t t = 0;
+      bool merged = false;
+      for (; t < count && !merged; ++t) {
+        const int64_t j = j0 + t;
+        if (probes[t].state == 1) { d[j] = -1; continue; }
+        if (probes[t].state == 0) continue;
+        ++st.comparisons;
+        const float dist = probes[t].dist;
+        d[j] = dist;
+        if (dist <= tau) {
+          st.merge_tau += dist;
+          st.row_distance += j - i;
+          ++st.merges;
+          g[j] = i;
+          if (use_pattern) pat.merge(j);
+          if (use_size) ++gsize;
+          merged = use_pattern || use_size;   // later distances of the window are stale only if the pattern or the size moved
+        }
       }
+      j0 += t;
+      window = merged ? kWindowMin : std::min(window * 2, kWindowMax);
     }
   }
 }
@@ -278,39 +383,122 @@ void run_queue(const Rows& m, P& pat, float tau, bool use_size, bool use_pattern
   std::vector<int64_t> pending(m.rows), kept;
   std::iota(pending.begin(), pending.end(), static_cast<int64_t>(0));
   kept.reserve(m.rows);
+  ScanPool pool(scan_threads());
+  std::vector<Probe> probes(static_cast<size_t>(kWindowMax));
   while (!pending.empty()) {
     const int64_t i = pending[0];
     pat.seed(i);
     int64_t gsize = 1;
     g[i] = i;
     kept.clear();
-    for (size_t q = 1; q < pending.size(); ++q) {
-      const int64_t j = pending[q];
-      if (pruned(d, i, j, tau)) { kept.push_back(j); continue; }
-      ++st.comparisons;
-      const float dist = pat.dist(j, gsize);
-      d[j] = dist;
-      if (dist > tau) { kept.push_back(j); continue; }
-      st.merge_tau += dist;
-      st.row_distance += j - i;
-      ++st.merges;
-      g[j] = i;
-      if (use_pattern) pat.merge(j);
-      if (use_size) ++gsize;
+    int64_t window = kWindowMin;
+    const int64_t n_pending = static_cast<int64_t>(pending.size());
+    for (int64_t q0 = 1; q0 < n_pending;) {
+      const int64_t count = std::min(window, n_pending - q0);
+      const int64_t* cand = pending.data() + q0;
+      // (every pending row is still without a group: g[j] == -1, state 0 cannot occur)
+      probe_window(pool, pat, gsize, i, tau, d, g, [cand](int64_t t) { return cand[t]; }, count, probes.data());
+      int64_t t = 0;
+      bool merged = false;
+      for (; t < count && !merged; ++t) {
+        const int64_t j = cand[t];
+        if (probes[t].state == 1) { d[j] = -1; kept.push_back(j); continue; }
+        ++st.comparisons;
+        const float dist = probes[t].dist;
+        d[j] = dist;
+        if (dist > tau) { kept.push_back(j); continue; }
+        st.merge_tau += dist;
+        st.row_distance += j - i;
+        ++st.merges;
+        g[j] = i;
+        if (use_pattern) pat.merge(j);
+        if (use_size) ++gsize;
+        merged = use_pattern || use_size;
+      }
+      q0 += t;
+      window = merged ? kWindowMin : std::min(window * 2, kWindowMax);
     }
     pending.swap(kept);
   }
 }
 
 // -a 5 runs IterativeBlockingKeeper (blocking.cpp:433-549, dispatched at :655).
+// Node storage of the candidate set of -a 5: one size class, a free list over slabs; the tree's shape and
+// every decision taken on it are those of std::set with std::allocator (the allocator only supplies memory).
+struct NodeArena {
+  size_t node_bytes = 0;
+  void* free_list = nullptr;
+  std::vector<void*> slabs;
+  ~NodeArena() { for (void* p : slabs) ::operator delete(p); }
+  void* take(size_t bytes) {
+    if (node_bytes == 0) node_bytes = (bytes + 15) / 16 * 16;
+    if (bytes > node_bytes) return nullptr;
+    if (!free_list) {
+      const size_t count = 4096;
+      char* slab = static_cast<char*>(::operator new(node_bytes * count));
+      slabs.push_back(slab);
+      for (size_t i = 0; i < count; ++i) {
+        void* p = slab + i * node_bytes;
+        *static_cast<void**>(p) = free_list;
+        free_list = p;
+      }
+    }
+    void* p = free_list;
+    free_list = *static_cast<void**>(p);
+    return p;
+  }
+  void give(void* p) {
+    *static_cast<void**>(p) = free_list;
+    free_list = p;
+  }
+};
+template <class T>
+struct PoolAllocator {
+  typedef T value_type;
+  NodeArena* arena;
+  explicit PoolAllocator(NodeArena* a) : arena(a) {}
+  template <class U> PoolAllocator(const PoolAllocator<U>& o) : arena(o.arena) {}
+  T* allocate(size_t n) {
+    void* p = n == 1 ? arena->take(sizeof(T)) : nullptr;
+    return static_cast<T*>(p ? p : ::operator new(n * sizeof(T)));
+  }
+  void deallocate(T* p, size_t n) {
+    if (n == 1 && sizeof(T) <= arena->node_bytes) arena->give(p); else ::operator delete(p);
+  }
+  template <class U> bool operator==(const PoolAllocator<U>& o) const { return arena == o.arena; }
+  template <class U> bool operator!=(const PoolAllocator<U>& o) const { return arena != o.arena; }
+};
+
+// What `it = s.end(); std::advance(it, k);` yields in libstdc++ for a non-empty set and k >= 1, in O(1).
+// Incrementing the header node (end()) goes to its right link -- the LARGEST element R -- and from there
+// down R's left links (_Rb_tree_increment); R has no right child, so by the red-black invariants its left
+// subtree is empty or one red leaf L.  From L the successor is R, from R it is the header again.  k steps
+// from end() therefore walk the cycle [L,] R, header, [L,] R, header, ...  (The reference does this walk
+// at blocking.cpp:509-511; it is undefined behaviour there and here it is reproduced, not repaired.
+// std::advance itself made 64 dependent pointer loads per rejected row: 94 % of the -a 5 time.)
+template <class S>
+typename S::iterator advance_from_end(S& s, size_t k) {
+  const std::_Rb_tree_node_base* hdr = s.end()._M_node;
+  const std::_Rb_tree_node_base* R = hdr->_M_right;
+  const std::_Rb_tree_node_base* L = R->_M_left;
+  const std::_Rb_tree_node_base* cyc[3];
+  size_t c = 0;
+  if (L) cyc[c++] = L;
+  cyc[c++] = R;
+  cyc[c++] = hdr;
+  return typename S::iterator(cyc[(k - 1) % c]);
+}
+
 template <class P>
 void run_keeper(const Rows& m, P& pat, float tau, int64_t max_rows, bool use_pattern, int64_t* g, Acc& st) {
-  typedef std::set<std::pair<float, int64_t>> Best;
+  typedef std::pair<float, int64_t> Cand;
+  typedef std::set<Cand, std::less<Cand>, PoolAllocator<Cand>> Best;   // same tree algorithms, nodes from a free list
+  NodeArena arena;
   std::vector<float> d = initial_distances(m.rows);
   std::vector<int64_t> members;
   for (int64_t i = 0; i < m.rows; ++i) {
     if (g[i] != -1) continue;
-    Best best;
+    Best best{std::less<Cand>(), PoolAllocator<Cand>(&arena)};
     members.assign(1, i);
     const int64_t gid = i + m.rows;
     pat.seed(i);
@@ -336,9 +524,7 @@ void run_keeper(const Rows& m, P& pat, float tau, int64_t max_rows, bool use_pat
           // The reference trims with advance(end(), k); erase(it, end()) (:509-511).  Walking
           // forward from end() is undefined; the same calls are made so that libstdc++ visits
           // the same tree nodes and erases the same elements.
-          Best::iterator it = best.end();
-          std::advance(it, static_cast<size_t>(max_rows) - members.size());
-          best.erase(it, best.end());
+          best.erase(advance_from_end(best, static_cast<size_t>(max_rows) - members.size()), best.end());
         }
       }
     }

@@ -92,6 +92,27 @@ def test_grouping_matches_oracle_and_reference(lib, oracle, tmp_path, flags):
             assert np.array_equal(g, rr["grouping"]), path
 
 
+@pytest.mark.parametrize("flags", [dict(a=3, b=32, t=0.6), dict(a=4, b=32, t=0.6), dict(a=5, b=32, B=32, t=0.6),
+                                   dict(a=4, b=16, t=0.4, g=1), dict(a=3, b=32, t=0.7, p=0)],
+                         ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()))
+def test_large_scans_match_the_reference(lib, oracle, tmp_path, flags):
+    """8192 rows: the -a 3 / -a 4 scans run in speculative windows on several host threads (windows of 2048 to
+    65536 candidates, thrown away at every merge), -a 5 trims its candidate set with the O(1) restatement of
+    libstdc++'s walk from end().  Grouping and counters against the unmodified reference build (else the oracle)."""
+    from oracle.oracle_py import Reference
+    r, c = synth.rmat_edges(13, 70000, seed=5)
+    r, c = synth.pin_shape(r, c, 8192, 8192)
+    path = str(tmp_path / "rmat13.el")
+    synth.write_el(path, r, c)
+    src = Reference() if Reference.available() else oracle
+    res = src.run(path, fill=False, P=1, **flags)
+    g, st = product_grouping(res, flags)
+    assert np.array_equal(g, res["grouping"])
+    assert st["comparison_counter"] == res["comparison_counter"] and st["merge_counter"] == res["merge_counter"]
+    assert same_float(st["average_merge_tau"], res["average_merge_tau"])
+    assert same_float(st["average_row_distance"], res["average_row_distance"])
+
+
 def test_blocking_then_fill_equals_reference_vbr(lib, oracle, tmp_path):
     """grouping -> VBR::fill_from_CSR_inplace through the product only, vs the oracle's arrays."""
     path = matrices(tmp_path)[0]
