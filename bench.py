@@ -317,7 +317,11 @@ def source_sha16():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "sparta_b200", "csrc")
-    for name in sorted(os.listdir(d)):
+    # the kernels, the tile scheduler and the layer that picks pipeline / tiles / launch attributes; the host-side
+    # builders (blocking, VBR fill, grouping cache) and the multi-GPU driver do not change what a launch does
+    kernel_side = ("abi.cu", "csr_kernel.cu", "csr_kernel.h", "pack_kernels.cu", "pack_kernels.h", "sched_types.h",
+                   "schedule.cpp", "schedule.h", "spmm_kernel.cu", "spmm_kernel.h")
+    for name in kernel_side:
         with open(os.path.join(d, name), "rb") as f:
             h.update(name.encode())
             h.update(f.read())

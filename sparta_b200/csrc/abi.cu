@@ -1528,6 +1528,7 @@ static int copy_c(sparta_handle* h, float* C, int64_t ld, int on_device, bool to
   if (ld < width) return fail(SPARTA_ERR_INVALID, "leading dimension of C too small");
   if (lines == 0 || width == 0) return SPARTA_OK;
   CU_TRY(cudaSetDevice(h->device));
+  h->chain_ok = false;   // something other than the handle's own multiply is about to sit on the stream
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice
                               : (to_handle ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
   if (to_handle)
@@ -1535,6 +1536,7 @@ static int copy_c(sparta_handle* h, float* C, int64_t ld, int on_device, bool to
   else
     CU_TRY(cudaMemcpy2DAsync(C, ld * sizeof(float), h->d_C, h->ldc * sizeof(float), width * sizeof(float), lines, kind, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  release_staged(h);
   return SPARTA_OK;
 }
 
@@ -1561,6 +1563,7 @@ int sparta_get_C_permuted(sparta_handle* h, float* C, int64_t ld, const int64_t*
     if (row_map[r] < 0 || row_map[r] >= out_rows) return fail(SPARTA_ERR_INVALID, "row_map entry out of range");
   if (rows == 0 || n == 0) return SPARTA_OK;
   CU_TRY(cudaSetDevice(h->device));
+  h->chain_ok = false;
   int64_t* d_map = nullptr;
   float* d_tmp = nullptr;
   CU_TRY(dev_alloc(&d_map, static_cast<size_t>(rows) * sizeof(int64_t), h->stream));
