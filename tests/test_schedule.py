@@ -187,16 +187,15 @@ def test_split_pieces_cover_every_chunk_once(oracle, lib, precision, esize, max_
     assert np.array_equal(Cm, oracle.vbr_multiply(v, Bm, n))
 
 
-@pytest.mark.parametrize("pair", [1, 2], ids=["single", "pair"])
-@pytest.mark.parametrize("tiles", [2, 4])
+@pytest.mark.parametrize("tiles,pair", [(2, 2), (4, 1)], ids=["2-tiles-pair", "4-tiles-single"])
 def test_wide_items_split_plan(oracle, lib, tiles, pair):
     """Wide items (2 / 4 column tiles per item) under a forced split plan: a zero job covers the whole wide tile,
     every piece of a (super-row, wide tile) is drained once per tile, the product is unchanged; n leaves the last
     wide tile partly (and for 4 tiles mostly) beyond B."""
     rng = np.random.default_rng(33)
-    heights = [64, 64, 64, 30, 64, 64, 17, 64]
+    heights = [64, 64, 30, 64, 17, 64]
     v = random_vbr(rng, len(heights), 4096, 64, heights, 0.5, values="int")
-    n = 700
+    n = 600
     Bm = rng.integers(-3, 4, size=(n, 4096)).astype(np.float32)
     plan = sparta_b200.vbr_plan(v["rows"], 4096, 64, v["row_part"], v["nzcount"], v["jab"], n, precision="bf16",
                                 cta_pair=pair, split_k=2, num_ctas=24, wide_tiles=tiles)
